@@ -1,0 +1,256 @@
+/*
+ * rar2d.h -- C-ABI of the B200-native hot path of RealisticAudioRaytracing2D.
+ *
+ * The reference has no FFI: its boundary between the C# components and the GPU kernels is Unity's
+ * string-keyed compute API (ComputeShader.SetInt/SetFloat/SetVector/SetBuffer/Dispatch,
+ * ComputeBuffer.SetData/GetData/SetCounterValue/CopyCount/Release, AsyncGPUReadback.Request).
+ * Each entry point below replaces one group of those call sites; the call site is cited as
+ * file:line relative to /root/reference/Assets/Script/.  A C# host binds these with [DllImport]
+ * (see INTEGRATION.md and csharp/RarNative.cs); tests bind them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host array and the library copies during
+ *     the call (the copy semantics of ComputeBuffer.SetData/GetData); device memory belongs to the
+ *     context;
+ *   - every function returns an int status, RAR_OK (0) on success, negative on failure, never throws;
+ *     rar_last_error() gives the message (the reference's convention is "null-guard and silently
+ *     skip", RayTraceManager.cs:52,119,222 -- a status code is the closest C equivalent);
+ *   - one caller thread per context (all reference GPU calls happen on the Unity main thread);
+ *   - trace and convolve_begin are asynchronous with respect to the host: they enqueue on the
+ *     context's CUDA stream and return; completion is polled (rar_poll), the analogue of
+ *     `while (!req.done) yield return null` (RayTraceManager.cs:115);
+ *   - there is no CPU fallback: every compute entry point fails with RAR_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef RAR2D_H
+#define RAR2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RAR_API __declspec(dllexport)
+#else
+#define RAR_API __attribute__((visibility("default")))
+#endif
+
+#define RAR_VERSION 100 /* 0.1.0 */
+
+enum {
+    RAR_OK = 0,
+    RAR_ERR_INVALID = -1,   /* bad argument */
+    RAR_ERR_CUDA = -2,      /* CUDA runtime failure / no usable device */
+    RAR_ERR_STATE = -3,     /* call out of order (no walls, slot not configured, ...) */
+    RAR_ERR_NOMEM = -4,
+    RAR_ERR_UNSUPPORTED = -5,
+    RAR_ERR_PENDING = -6    /* ticket not complete yet (convolve_end before done) */
+};
+
+/* Helpers/SceneHelper.cs:15-22 `Segment` (LayoutKind.Sequential) == Raytrace2D.compute:19-22 `Wall`
+ * with the nested AudioMat (Helpers/SceneHelper.cs:8-14 == Raytrace2D.compute:12-17).  40 bytes. */
+typedef struct rar_segment {
+    float start[2];
+    float end[2];
+    float normal[2];
+    float absorption;
+    float scattering;
+    float transmission;
+    float ior;
+} rar_segment;
+
+/* RayTraceManager.cs:43 / Raytrace2D.compute:24-28 `RayInfo`.  16 bytes. */
+typedef struct rar_ray_info {
+    float time_delay;
+    float energy;
+    float hit_point[2];
+} rar_ray_info;
+
+/* Which ray produced a rar_ray_info (parity tooling; the reference's append buffer is unordered). */
+typedef struct rar_hit_key {
+    uint32_t ray;
+    uint16_t bounce;
+    uint16_t kind; /* 0 direct listener crossing (Raytrace2D.compute:74-84), 1 next-event estimate (:101-119) */
+} rar_hit_key;
+
+#define RAR_FLAG_EXACT_RAY_COUNT 1u /* trace exactly ray_count rays; default reproduces the reference's
+                                       unguarded dispatch of ceil(rayCount/64)*64 threads
+                                       (Raytrace2D.compute:49-52, Helpers/ComputeHelper.cs:27-31) */
+#define RAR_FLAG_COUNT_TESTS 2u     /* also count ray-segment tests (slower; for measurement and parity) */
+
+/* The uniforms of Trace and ProcessHits: Raytrace2D.compute:5-10,36 set at RayTraceManager.cs:191-201
+ * and :227-228; ImpulseLength from RayTraceManager.cs:174.  `bands`/`time_divisor` carry the banded
+ * layout of RaytraceOcclusion2D.compute:241-248 (WindowSize); ray_begin/ray_end shard one dispatch
+ * across GPUs by contiguous thread-id range. */
+typedef struct rar_trace_params {
+    float source_pos[2];
+    float listener_pos[2];
+    float listener_radius;
+    float speed_of_sound;
+    float input_gain;
+    int32_t max_bounce_count;
+    uint32_t rng_state_offset; /* Time.frameCount, RayTraceManager.cs:197 */
+    int32_t ray_count;         /* the `rayCount` uniform: denominator of the launch angle */
+    int32_t debug_ray_count;
+    int32_t sample_rate;
+    int32_t impulse_length;    /* number of time bins */
+    int32_t bands;             /* 1 = broadband; >1: slot layout IR[bin*bands + band] */
+    float time_divisor;        /* 1: bin=(int)(t*SampleRate); W: bin=(int)(t*SampleRate/W) */
+    uint32_t flags;            /* RAR_FLAG_* */
+    int64_t ray_begin;         /* thread-id range [ray_begin, ray_end) traced by this call; */
+    int64_t ray_end;           /* (0,0) = the whole dispatch */
+} rar_trace_params;
+
+typedef struct rar_counters {
+    uint64_t ray_bounces;   /* iterations of the bounce loop, Raytrace2D.compute:66 */
+    uint64_t nearest_tests; /* intersect() evaluations of the nearest-hit loop (:69-72) */
+    uint64_t shadow_tests;  /* intersect() evaluations of checkVis (:40-47) with its early exit */
+    uint64_t direct_hits;
+    uint64_t nee_hits;
+} rar_counters;
+
+typedef struct rar_context rar_context;
+typedef struct rar_convolver rar_convolver;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+RAR_API int rar_version(void);
+
+/* Creates a context on CUDA device `device` with its own non-blocking stream.  Replaces the implicit
+ * Unity graphics device.  Two IR slots (ping/pong, RayTraceManager.cs:36,212-218) exist from creation
+ * and read as zero until configured by rar_ir_clear. */
+RAR_API int rar_create(int device, rar_context **out);
+
+/* RayTraceManager.cs:281 OnDestroy -> ComputeHelper.Release(...) (Helpers/ComputeHelper.cs:209-247).
+ * NULL is accepted, like `buffer?.Release()`. */
+RAR_API int rar_destroy(rar_context *ctx);
+
+/* Message of the most recent failure on this context (or of rar_create when ctx is NULL). */
+RAR_API const char *rar_last_error(const rar_context *ctx);
+
+/* Plumbing for hosts that already own a CUDA stream (e.g. to order an NCCL all-reduce after the
+ * trace): all later work of the context is enqueued on `cuda_stream` (a cudaStream_t); NULL restores
+ * the context's own stream. */
+RAR_API int rar_set_stream(rar_context *ctx, void *cuda_stream);
+
+/* Blocks until everything enqueued on the context has finished. */
+RAR_API int rar_sync(rar_context *ctx);
+
+/* ---- geometry ------------------------------------------------------------------------------- */
+
+/* RayTraceManager.cs:246-250 UpdateGeometry -> ComputeHelper.CreateStructuredBuffer(ref wallBuffer,
+ * activeSegments) (Helpers/ComputeHelper.cs:114-125): copy-in of n x 40 B AoS segments, reallocating
+ * when the count grows.  The library re-lays them out for the kernels (endpoint plane + material
+ * planes).  n may be 0. */
+RAR_API int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n);
+
+/* Build extension for BASELINE config 3: per-wall absorption for `bands` frequency bands, row-major
+ * [n][bands]; n must equal the current wall count. */
+RAR_API int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int32_t n, int32_t bands);
+
+/* ---- impulse-response slots ------------------------------------------------------------------ */
+
+/* RayTraceManager.cs:169-177 ResetIR -> ClearImpulse (Raytrace2D.compute:167-172), plus the buffer
+ * (re)creation of GetActiveIRBuffer (:212-218): slot becomes impulse_length x bands zeros (64-bit
+ * fixed point, Q23.40).  Asynchronous. */
+RAR_API int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length, int32_t bands);
+
+/* Float view of a slot: the un-normalised sum over the frames accumulated so far, the same quantity
+ * the reference's float ImpulseResponse buffer holds (division by accumCount happens in the
+ * convolution, AudioConvolve.compute:30).  n = impulse_length*bands values.  Blocking. */
+RAR_API int rar_ir_read(rar_context *ctx, int32_t slot, float *out, int64_t n);
+
+/* The slot's exact contents, for bit-exact comparison.  Blocking. */
+RAR_API int rar_ir_read_fixed(rar_context *ctx, int32_t slot, int64_t *out, int64_t n);
+
+/* Overwrites a slot with quantised host data (tests and externally supplied IRs).  Blocking. */
+RAR_API int rar_ir_write(rar_context *ctx, int32_t slot, const float *ir, int32_t impulse_length, int32_t bands);
+
+/* Device address and word count of a slot's int64 histogram, so the host plumbing can hand it to a
+ * collective (one ncclAllReduce(sum, int64) across the GPUs that traced disjoint ray ranges). */
+RAR_API int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr, int64_t *n_words);
+
+/* ---- ray tracing ------------------------------------------------------------------------------ */
+
+/* RayTraceManager.cs:179-210 RunSimulation (Trace dispatch :205) fused with :220-232
+ * OnSimulationFinished (ProcessHits dispatch :231): traces the rays and adds every arrival straight
+ * into `slot` -- no hit buffer, no hit-count round trip.  Asynchronous.  params->impulse_length and
+ * params->bands must match the slot's configuration. */
+RAR_API int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot);
+
+/* Same trace, but the arrivals are returned instead of binned: the contents of the reference's
+ * rayInfoBuffer (AppendStructuredBuffer<RayInfo>, Raytrace2D.compute:82,116), unordered, with the
+ * producing ray/bounce in `keys` (may be NULL).  *count receives the number produced (may exceed
+ * capacity; only min(count,capacity) are stored).  Blocking; not a timed path. */
+RAR_API int rar_trace_hits(rar_context *ctx, const rar_trace_params *params, rar_ray_info *hits,
+                           rar_hit_key *keys, int64_t capacity, int64_t *count);
+
+/* Totals accumulated by traces run with RAR_FLAG_COUNT_TESTS since the last reset.  Blocking. */
+RAR_API int rar_get_counters(rar_context *ctx, rar_counters *out, int32_t reset);
+
+/* RayTraceManager.cs:183,204,207: the debugRays buffer of the most recent rar_trace, float4 per
+ * vertex, max(100, debug_ray_count) * (max_bounce_count+1) entries.  Blocking. */
+RAR_API int rar_get_debug_rays(rar_context *ctx, float *out_xyzw, int64_t n_float4);
+
+/* ---- convolution ------------------------------------------------------------------------------- */
+
+/* RayTraceManager.cs:91-123 ProcessChunk and RayTraceManagerComplex.cs:170-227 BakeAudio: the
+ * AudioConvolve kernel (AudioConvolve.compute:13-31) on `in` and the IR in `slot` (band 0 of a
+ * banded slot is not supported here: bands must be 1):
+ *   out[n] = (1/accum_count) * sum_k in[k]*ir[n-k] over |in[k]| > 1e-4,  n in [0, in_len+ir_len),
+ *   all zeros when accum_count <= 0.
+ * Computed as a uniformly partitioned overlap-save FFT convolution (block 256).
+ * rar_convolve is the blocking form (ComputeBuffer.GetData, RayTraceManagerComplex.cs:209). */
+RAR_API int rar_convolve(rar_context *ctx, int32_t slot, const float *in, int32_t in_len, int32_t accum_count,
+                         float *out, int32_t out_len);
+
+/* Asynchronous form: SetData + Dispatch + AsyncGPUReadback.Request (RayTraceManager.cs:100-114).
+ * `in` is copied before returning.  *ticket identifies the request. */
+RAR_API int rar_convolve_begin(rar_context *ctx, int32_t slot, const float *in, int32_t in_len,
+                               int32_t accum_count, int32_t *ticket);
+
+/* `req.done` (RayTraceManager.cs:115): 1 = complete, 0 = still running, negative = failed. */
+RAR_API int rar_poll(rar_context *ctx, int32_t ticket);
+
+/* `req.GetData<float>().CopyTo(result)` (RayTraceManager.cs:121): waits if necessary, copies the
+ * in_len+ir_len results and retires the ticket. */
+RAR_API int rar_convolve_end(rar_context *ctx, int32_t ticket, float *out, int32_t out_len);
+
+/* ---- batched streaming convolver (BASELINE config 5) --------------------------------------------
+ * n_streams independent 48 kHz streams, each convolved with its own IR by uniformly partitioned
+ * overlap-save: every call to process consumes `block` new samples per stream and produces `block`
+ * output samples per stream.  State (frequency-domain delay lines, IR spectra) is device resident. */
+RAR_API int rar_conv_create(rar_context *ctx, int32_t n_streams, int32_t block, int32_t max_ir_len,
+                            rar_convolver **out);
+RAR_API int rar_conv_destroy(rar_convolver *conv);
+/* IR of one stream from host memory; values are multiplied by `scale` (1/accumCount). */
+RAR_API int rar_conv_set_ir(rar_convolver *conv, int32_t stream, const float *ir, int32_t ir_len, float scale);
+/* IR of one stream taken on the device from a traced slot (bands == 1), scaled by 1/accum_count. */
+RAR_API int rar_conv_set_ir_from_slot(rar_convolver *conv, int32_t stream, int32_t slot, int32_t accum_count);
+/* Zeroes the delay lines (start of a stream, AudioManager.StartStreaming). */
+RAR_API int rar_conv_reset(rar_convolver *conv);
+/* One block for every stream: in/out are host arrays [n_streams][block].  Blocking; copies included. */
+RAR_API int rar_conv_process(rar_convolver *conv, const float *in, float *out);
+/* Same with device-resident in/out (cudaMalloc'ed by the caller); asynchronous on the context stream. */
+RAR_API int rar_conv_process_device(rar_convolver *conv, const float *d_in, float *d_out);
+/* Algorithmic HBM bytes one process call moves (delay-line + IR spectra reads, spectrum write, I/O). */
+RAR_API int64_t rar_conv_bytes_per_block(const rar_convolver *conv);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+
+/* Device facts for the bench line: SM count, max SM clock (kHz), shared memory per block opt-in. */
+RAR_API int rar_device_info(rar_context *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int32_t *smem_optin_bytes);
+
+/* Measures the FP32 FMA issue peak of the device with a register-only FFMA loop (lane-ops/s, one
+ * fused multiply-add = 1 lane-op): the denominator of the ray stage's roofline. */
+RAR_API int rar_measure_fp32_peak(rar_context *ctx, double *lane_ops_per_s);
+
+/* Number of kernels this library has launched on the context since creation (bench: gpu_launches). */
+RAR_API int64_t rar_launch_count(const rar_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAR2D_H */
