@@ -1,0 +1,316 @@
+"""ctypes binding of the C-ABI in include/rar2d.h (librar2d.so, built in-tree by build.py).
+
+This is the only way the Python host code reaches the compute path.  There is no fallback: if the
+shared library is missing, or no B200-class CUDA device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librar2d.so")
+
+RAR_OK = 0
+RAR_FLAG_EXACT_RAY_COUNT = 1
+RAR_FLAG_COUNT_TESTS = 2
+
+# include/rar2d.h rar_segment / rar_ray_info / rar_hit_key
+SEGMENT_DTYPE = np.dtype(
+    [("start", "<f4", (2,)), ("end", "<f4", (2,)), ("normal", "<f4", (2,)),
+     ("absorption", "<f4"), ("scattering", "<f4"), ("transmission", "<f4"), ("ior", "<f4")]
+)
+RAY_INFO_DTYPE = np.dtype([("time_delay", "<f4"), ("energy", "<f4"), ("hit_point", "<f4", (2,))])
+HIT_KEY_DTYPE = np.dtype([("ray", "<u4"), ("bounce", "<u2"), ("kind", "<u2")])
+assert SEGMENT_DTYPE.itemsize == 40 and RAY_INFO_DTYPE.itemsize == 16 and HIT_KEY_DTYPE.itemsize == 8
+
+
+class TraceParams(C.Structure):
+    """include/rar2d.h rar_trace_params."""
+    _fields_ = [
+        ("source_pos", C.c_float * 2), ("listener_pos", C.c_float * 2),
+        ("listener_radius", C.c_float), ("speed_of_sound", C.c_float), ("input_gain", C.c_float),
+        ("max_bounce_count", C.c_int32), ("rng_state_offset", C.c_uint32), ("ray_count", C.c_int32),
+        ("debug_ray_count", C.c_int32), ("sample_rate", C.c_int32), ("impulse_length", C.c_int32),
+        ("bands", C.c_int32), ("time_divisor", C.c_float), ("flags", C.c_uint32),
+        ("ray_begin", C.c_int64), ("ray_end", C.c_int64),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [("ray_bounces", C.c_uint64), ("nearest_tests", C.c_uint64), ("shadow_tests", C.c_uint64),
+                ("direct_hits", C.c_uint64), ("nee_hits", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+# name -> (restype, argtypes).  Every symbol include/rar2d.h declares.
+_p, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SYMBOLS = {
+    "rar_version": (C.c_int, []),
+    "rar_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "rar_destroy": (C.c_int, [_p]),
+    "rar_last_error": (C.c_char_p, [_p]),
+    "rar_set_stream": (C.c_int, [_p, _p]),
+    "rar_sync": (C.c_int, [_p]),
+    "rar_set_walls": (C.c_int, [_p, _p, _i32]),
+    "rar_set_wall_band_absorption": (C.c_int, [_p, _p, _i32, _i32]),
+    "rar_ir_clear": (C.c_int, [_p, _i32, _i32, _i32]),
+    "rar_ir_read": (C.c_int, [_p, _i32, _p, _i64]),
+    "rar_ir_read_fixed": (C.c_int, [_p, _i32, _p, _i64]),
+    "rar_ir_write": (C.c_int, [_p, _i32, _p, _i32, _i32]),
+    "rar_ir_device_ptr": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64)]),
+    "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
+    "rar_trace_hits": (C.c_int, [_p, C.POINTER(TraceParams), _p, _p, _i64, C.POINTER(_i64)]),
+    "rar_get_counters": (C.c_int, [_p, C.POINTER(Counters), _i32]),
+    "rar_get_debug_rays": (C.c_int, [_p, _p, _i64]),
+    "rar_convolve": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i32]),
+    "rar_convolve_begin": (C.c_int, [_p, _i32, _p, _i32, _i32, C.POINTER(_i32)]),
+    "rar_poll": (C.c_int, [_p, _i32]),
+    "rar_convolve_end": (C.c_int, [_p, _i32, _p, _i32]),
+    "rar_conv_create": (C.c_int, [_p, _i32, _i32, _i32, C.POINTER(_p)]),
+    "rar_conv_destroy": (C.c_int, [_p]),
+    "rar_conv_set_ir": (C.c_int, [_p, _i32, _p, _i32, _f32]),
+    "rar_conv_set_ir_from_slot": (C.c_int, [_p, _i32, _i32, _i32]),
+    "rar_conv_reset": (C.c_int, [_p]),
+    "rar_conv_process": (C.c_int, [_p, _p, _p]),
+    "rar_conv_process_device": (C.c_int, [_p, _p, _p]),
+    "rar_conv_bytes_per_block": (_i64, [_p]),
+    "rar_device_info": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "rar_measure_fp32_peak": (C.c_int, [_p, C.POINTER(C.c_double)]),
+    "rar_launch_count": (_i64, [_p]),
+}
+
+_lib = None
+
+
+class RarError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rar2d error {code}: {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Loads librar2d.so and declares every prototype.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RarError(-2, f"{LIB_PATH} is missing: build it with `python -m realisticaudioraytracing2d_b200.build` "
+                               "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(ctx, rc: int) -> int:
+    if rc < 0:
+        msg = load().rar_last_error(ctx)
+        raise RarError(rc, msg.decode("utf-8", "replace") if msg else "")
+    return rc
+
+
+def make_trace_params(source, listener, listener_radius=0.5, speed_of_sound=343.0, input_gain=1.0,
+                      max_bounce_count=5, rng_state_offset=1, ray_count=1000, debug_ray_count=0,
+                      sample_rate=48000, impulse_length=96000, bands=1, time_divisor=1.0, flags=0,
+                      ray_begin=0, ray_end=0) -> TraceParams:
+    p = TraceParams()
+    p.source_pos[0], p.source_pos[1] = float(source[0]), float(source[1])
+    p.listener_pos[0], p.listener_pos[1] = float(listener[0]), float(listener[1])
+    p.listener_radius, p.speed_of_sound, p.input_gain = listener_radius, speed_of_sound, input_gain
+    p.max_bounce_count, p.rng_state_offset, p.ray_count = max_bounce_count, rng_state_offset & 0xFFFFFFFF, ray_count
+    p.debug_ray_count, p.sample_rate, p.impulse_length = debug_ray_count, sample_rate, impulse_length
+    p.bands, p.time_divisor, p.flags = bands, time_divisor, flags
+    p.ray_begin, p.ray_end = ray_begin, ray_end
+    return p
+
+
+class Context:
+    """Thin object wrapper over a rar_context*; methods map 1:1 onto the C entry points."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = _p()
+        rc = self._lib.rar_create(device, C.byref(h))
+        if rc < 0:
+            msg = self._lib.rar_last_error(None)
+            raise RarError(rc, msg.decode() if msg else "")
+        self._h = h
+        self.device = device
+
+    # lifetime ---------------------------------------------------------------------------------
+    def destroy(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.rar_destroy(self._h)
+            self._h = None
+
+    close = destroy
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.destroy()
+
+    def _ck(self, rc):
+        return check(self._h, rc)
+
+    def set_stream(self, cuda_stream_ptr) -> None:
+        self._ck(self._lib.rar_set_stream(self._h, _p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def sync(self) -> None:
+        self._ck(self._lib.rar_sync(self._h))
+
+    # geometry ---------------------------------------------------------------------------------
+    def set_walls(self, segments: np.ndarray) -> None:
+        seg = np.ascontiguousarray(segments)
+        if seg.dtype.itemsize != 40:
+            raise ValueError("walls must be 40-byte Segment records")
+        self._ck(self._lib.rar_set_walls(self._h, seg.ctypes.data if len(seg) else None, len(seg)))
+
+    def set_wall_band_absorption(self, table: np.ndarray) -> None:
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        self._ck(self._lib.rar_set_wall_band_absorption(self._h, t.ctypes.data if t.size else None, t.shape[0], t.shape[1]))
+
+    # IR slots ---------------------------------------------------------------------------------
+    def ir_clear(self, slot: int, impulse_length: int, bands: int = 1) -> None:
+        self._ck(self._lib.rar_ir_clear(self._h, slot, impulse_length, bands))
+
+    def ir_read(self, slot: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self._lib.rar_ir_read(self._h, slot, out.ctypes.data, n))
+        return out
+
+    def ir_read_fixed(self, slot: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int64)
+        self._ck(self._lib.rar_ir_read_fixed(self._h, slot, out.ctypes.data, n))
+        return out
+
+    def ir_write(self, slot: int, ir: np.ndarray, bands: int = 1) -> None:
+        a = np.ascontiguousarray(ir, dtype=np.float32)
+        self._ck(self._lib.rar_ir_write(self._h, slot, a.ctypes.data if a.size else None, a.size // bands, bands))
+
+    def ir_device_ptr(self, slot: int):
+        ptr, n = _p(), _i64()
+        self._ck(self._lib.rar_ir_device_ptr(self._h, slot, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    # trace ------------------------------------------------------------------------------------
+    def trace(self, params: TraceParams, slot: int) -> None:
+        self._ck(self._lib.rar_trace(self._h, C.byref(params), slot))
+
+    def trace_hits(self, params: TraceParams, capacity: int):
+        hits = np.zeros(capacity, dtype=RAY_INFO_DTYPE)
+        keys = np.zeros(capacity, dtype=HIT_KEY_DTYPE)
+        cnt = _i64()
+        self._ck(self._lib.rar_trace_hits(self._h, C.byref(params), hits.ctypes.data, keys.ctypes.data, capacity, C.byref(cnt)))
+        n = min(cnt.value, capacity)
+        return hits[:n], keys[:n], cnt.value
+
+    def get_counters(self, reset: bool = True) -> dict:
+        c = Counters()
+        self._ck(self._lib.rar_get_counters(self._h, C.byref(c), 1 if reset else 0))
+        return c.as_dict()
+
+    def get_debug_rays(self, n_float4: int) -> np.ndarray:
+        out = np.zeros((n_float4, 4), dtype=np.float32)
+        self._ck(self._lib.rar_get_debug_rays(self._h, out.ctypes.data, n_float4))
+        return out
+
+    # convolution ------------------------------------------------------------------------------
+    def convolve(self, slot: int, samples: np.ndarray, accum_count: int, ir_len: int) -> np.ndarray:
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        out = np.empty(len(x) + ir_len, dtype=np.float32)
+        self._ck(self._lib.rar_convolve(self._h, slot, x.ctypes.data if len(x) else None, len(x), accum_count,
+                                        out.ctypes.data, len(out)))
+        return out
+
+    def convolve_begin(self, slot: int, samples: np.ndarray, accum_count: int) -> int:
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        t = _i32(-1)
+        self._ck(self._lib.rar_convolve_begin(self._h, slot, x.ctypes.data if len(x) else None, len(x), accum_count, C.byref(t)))
+        return t.value
+
+    def poll(self, ticket: int) -> bool:
+        return self._ck(self._lib.rar_poll(self._h, ticket)) == 1
+
+    def convolve_end(self, ticket: int, out_len: int) -> np.ndarray:
+        out = np.empty(out_len, dtype=np.float32)
+        self._ck(self._lib.rar_convolve_end(self._h, ticket, out.ctypes.data, out_len))
+        return out
+
+    # measurement ------------------------------------------------------------------------------
+    def device_info(self) -> dict:
+        a, b, c = _i32(), _i32(), _i32()
+        self._ck(self._lib.rar_device_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sm_count": a.value, "sm_clock_khz": b.value, "smem_optin_bytes": c.value}
+
+    def measure_fp32_peak(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.rar_measure_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
+    def launch_count(self) -> int:
+        return int(self._lib.rar_launch_count(self._h))
+
+
+class Convolver:
+    """rar_convolver*: the batched streaming partitioned convolver (BASELINE config 5)."""
+
+    def __init__(self, ctx: Context, n_streams: int, block: int, max_ir_len: int):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = _p()
+        ctx._ck(self._lib.rar_conv_create(ctx._h, n_streams, block, max_ir_len, C.byref(h)))
+        self._h = h
+        self.n_streams, self.block, self.max_ir_len = n_streams, block, max_ir_len
+
+    def destroy(self) -> None:
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.rar_conv_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def set_ir(self, stream: int, ir: np.ndarray, scale: float = 1.0) -> None:
+        a = np.ascontiguousarray(ir, dtype=np.float32)
+        self._ctx._ck(self._lib.rar_conv_set_ir(self._h, stream, a.ctypes.data if a.size else None, a.size, scale))
+
+    def set_ir_from_slot(self, stream: int, slot: int, accum_count: int) -> None:
+        self._ctx._ck(self._lib.rar_conv_set_ir_from_slot(self._h, stream, slot, accum_count))
+
+    def reset(self) -> None:
+        self._ctx._ck(self._lib.rar_conv_reset(self._h))
+
+    def process(self, block_in: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(block_in, dtype=np.float32)
+        if x.shape != (self.n_streams, self.block):
+            raise ValueError(f"expected input of shape {(self.n_streams, self.block)}")
+        out = np.empty_like(x)
+        self._ctx._ck(self._lib.rar_conv_process(self._h, x.ctypes.data, out.ctypes.data))
+        return out
+
+    def process_host_ptr(self, in_ptr: int, out_ptr: int) -> None:
+        self._ctx._ck(self._lib.rar_conv_process(self._h, _p(in_ptr), _p(out_ptr)))
+
+    def process_device(self, d_in_ptr: int, d_out_ptr: int) -> None:
+        self._ctx._ck(self._lib.rar_conv_process_device(self._h, _p(d_in_ptr), _p(d_out_ptr)))
+
+    def bytes_per_block(self) -> int:
+        return int(self._lib.rar_conv_bytes_per_block(self._h))

@@ -1,0 +1,372 @@
+// conv_kernels.cu -- uniformly partitioned overlap-save FFT convolution for sm_100a.
+//
+// Replaces AudioConvolve.compute:13-31 (direct-form O(N*M), one thread per output sample).  Block
+// B = 256 samples, window 2B = 512, IR split into partitions of B taps.  With X[j] the spectrum of
+// the input window ending at block j and H[p] the spectrum of IR partition p,
+//        Y[j] = sum_p X[j-p] * H[p],     output block j = last B samples of irfft(Y[j]).
+// The FFTs are hand-written shared-memory radix-4 Stockham transforms (rar_fft.cuh); the
+// complex-multiply-accumulate over partitions streams both spectra from HBM with 16-byte loads and
+// is the bandwidth-bound kernel of the streaming convolver (BASELINE config 5: 2 x 1875 x 2 KB per
+// stream per block).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <mutex>
+
+#include "rar_fft.cuh"
+#include "rar_internal.h"
+
+namespace rar {
+namespace {
+
+constexpr int kB = 256;            // block
+constexpr int kSub = 4;            // transforms per CTA in the FFT kernels
+constexpr float kConvEps = 1e-4f;  // Common.hlsl:4, used by AudioConvolve.compute:25
+
+__device__ f2 g_tw[kFftM];           // exp(-2 pi i k / 256)
+__device__ f2 g_tw2[kFftM / 2 + 1];  // exp(-2 pi i k / 512)
+
+struct FftSmem {
+    f2 a[kSub][kFftM];
+    f2 b[kSub][kFftM];
+    f2 tw[kFftM];
+    f2 tw2[kFftM / 2 + 1];
+};
+
+__device__ __forceinline__ void load_tables(FftSmem &s) {
+    for (int k = threadIdx.x; k < kFftM; k += blockDim.x) s.tw[k] = g_tw[k];
+    for (int k = threadIdx.x; k <= kFftM / 2; k += blockDim.x) s.tw2[k] = g_tw2[k];
+}
+
+// Four radix-4 passes a -> b -> a -> b -> a; the result is in a.  Block-wide barriers between passes.
+__device__ __forceinline__ void fft256_inplace(f2 *a, f2 *b, int i, const f2 *tw, bool inverse) {
+    fft_pass_r4(a, b, i, 1, tw, inverse);
+    __syncthreads();
+    fft_pass_r4(b, a, i, 4, tw, inverse);
+    __syncthreads();
+    fft_pass_r4(a, b, i, 16, tw, inverse);
+    __syncthreads();
+    fft_pass_r4(b, a, i, 64, tw, inverse);
+    __syncthreads();
+}
+
+// Loads the real window w[m] = src(first + m), m in [0, 512), packed as z[n] = (w[2n], w[2n+1]), forward
+// transforms it and leaves the packed half spectrum in s.b[sub].  `fetch(t)` returns sample t or 0.
+template <class Fetch>
+__device__ __forceinline__ void rfft512_to_b(FftSmem &s, int sub, int i, Fetch fetch) {
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int n = i + 64 * m;
+        s.a[sub][n] = f2{fetch(2 * n), fetch(2 * n + 1)};
+    }
+    __syncthreads();
+    fft256_inplace(s.a[sub], s.b[sub], i, s.tw, false);
+    for (int k = i; k <= kFftM / 2; k += 64) rfft_split(s.a[sub], s.b[sub], k, s.tw2);
+    __syncthreads();
+}
+
+// Packed half spectrum in s.b[sub] -> real window; afterwards s.a[sub][n] = (w[2n], w[2n+1]) * M.
+__device__ __forceinline__ void irfft512_from_b(FftSmem &s, int sub, int i) {
+    for (int k = i; k <= kFftM / 2; k += 64) irfft_merge(s.b[sub], s.a[sub], k, s.tw2);
+    __syncthreads();
+    fft256_inplace(s.a[sub], s.b[sub], i, s.tw, true);
+}
+
+__global__ void fixed_to_float_kernel(const long long *__restrict__ hist, float *__restrict__ out, long long n, float scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = ((float)hist[i] * 9.094947017729282e-13f) * scale;
+}
+
+__global__ void float_to_fixed_kernel(const float *__restrict__ in, long long *__restrict__ hist, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        hist[i] = quantize_energy(in[i]);
+}
+
+// H[p] = rfft([ir[pB .. pB+B), 0 x B])
+__global__ void __launch_bounds__(64 * kSub) ir_spectra_kernel(const float *__restrict__ ir, int ir_len, f2 *__restrict__ H,
+                                                                int n_part) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int p = blockIdx.x * kSub + sub;
+    load_tables(s);
+    const long long first = (long long)p * kB;
+    rfft512_to_b(s, sub, i, [&](int t) -> float {
+        const long long g = first + t;
+        return (p < n_part && t < kB && g < ir_len) ? ir[g] : 0.0f;
+    });
+    if (p < n_part) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) H[(size_t)p * kFftM + i + 64 * m] = s.b[sub][i + 64 * m];
+    }
+}
+
+// X[j] = rfft(x[(j-1)B .. (j+1)B)) with out-of-range samples and |x| <= eps samples as zero.
+__global__ void __launch_bounds__(64 * kSub) input_spectra_kernel(const float *__restrict__ x, int x_len, f2 *__restrict__ X,
+                                                                   int n_xwin) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int j = blockIdx.x * kSub + sub;
+    load_tables(s);
+    const long long first = ((long long)j - 1) * kB;
+    rfft512_to_b(s, sub, i, [&](int t) -> float {
+        const long long g = first + t;
+        if (j >= n_xwin || g < 0 || g >= x_len) return 0.0f;
+        const float v = x[g];
+        return fabsf(v) > kConvEps ? v : 0.0f;
+    });
+    if (j < n_xwin) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) X[(size_t)j * kFftM + i + 64 * m] = s.b[sub][i + 64 * m];
+    }
+}
+
+// Accumulators of one float4 (two packed bins).  Bin A keeps a.x*b.x and a.y*b.y apart so that packed
+// bin 0 (DC, Nyquist) can be finished as two real products.
+struct Acc4 {
+    float ac, bd, im, re1, im1;
+};
+__device__ __forceinline__ void cmac4(Acc4 &s, const float4 x, const float4 h) {
+    s.ac = fmaf(x.x, h.x, s.ac);
+    s.bd = fmaf(x.y, h.y, s.bd);
+    s.im = fmaf(x.x, h.y, fmaf(x.y, h.x, s.im));
+    s.re1 = fmaf(x.z, h.z, fmaf(-x.w, h.w, s.re1));
+    s.im1 = fmaf(x.z, h.w, fmaf(x.w, h.z, s.im1));
+}
+__device__ __forceinline__ float4 finish4(const Acc4 &s, bool packed_bin0) {
+    return packed_bin0 ? make_float4(s.ac, s.bd, s.re1, s.im1) : make_float4(s.ac - s.bd, s.im, s.re1, s.im1);
+}
+
+// Y[j] = sum_{p} X[j-p] * H[p] over the valid p; one CTA of 128 threads per output block.
+__global__ void __launch_bounds__(128) block_cmac_kernel(const float4 *__restrict__ X, int n_xwin, const float4 *__restrict__ H,
+                                                          int n_part, float4 *__restrict__ Y) {
+    const int j = blockIdx.x, t = threadIdx.x;
+    int p_lo = j - (n_xwin - 1);
+    if (p_lo < 0) p_lo = 0;
+    int p_hi = j < n_part - 1 ? j : n_part - 1;
+    Acc4 s = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int p = p_lo; p <= p_hi; p++) cmac4(s, __ldg(X + (size_t)(j - p) * 128 + t), __ldg(H + (size_t)p * 128 + t));
+    Y[(size_t)j * 128 + t] = finish4(s, t == 0);
+}
+
+// out[jB + i] = irfft(Y[j])[B + i] * scale
+__global__ void __launch_bounds__(64 * kSub) output_blocks_kernel(const f2 *__restrict__ Y, int n_out_blocks, float *__restrict__ out,
+                                                                   int out_len, float scale) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int j = blockIdx.x * kSub + sub;
+    load_tables(s);
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        s.b[sub][i + 64 * m] = j < n_out_blocks ? Y[(size_t)j * kFftM + i + 64 * m] : f2{0.f, 0.f};
+    __syncthreads();
+    irfft512_from_b(s, sub, i);
+    if (j < n_out_blocks) {
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const int n = 128 + i + 64 * m;  // second half of the window
+            const long long o = (long long)j * kB + 2 * (n - 128);
+            const f2 v = s.a[sub][n];
+            // sample out_len-1 lies beyond the N+M-1 samples of the linear convolution: the reference's
+            // loop is empty there (AudioConvolve.compute:19-20) and writes an exact 0.
+            if (o < out_len) out[o] = o == out_len - 1 ? 0.0f : v.x * scale;
+            if (o + 1 < out_len) out[o + 1] = o + 1 == out_len - 1 ? 0.0f : v.y * scale;
+        }
+    }
+}
+
+// ---- streaming convolver ------------------------------------------------------------------------------
+
+// Window = [prev block | new block] per stream -> fdl[s][head]; prev <- new (after eps zeroing).
+__global__ void __launch_bounds__(64 * kSub) stream_input_kernel(const float *__restrict__ in, float *__restrict__ prev,
+                                                                  f2 *__restrict__ fdl, int n_streams, int n_part, int head) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int st = blockIdx.x * kSub + sub;
+    load_tables(s);
+    const bool on = st < n_streams;
+    const float *pv = prev + (size_t)st * kB;
+    const float *nw = in + (size_t)st * kB;
+    rfft512_to_b(s, sub, i, [&](int t) -> float {
+        if (!on) return 0.0f;
+        if (t < kB) return pv[t];
+        const float v = nw[t - kB];
+        return fabsf(v) > kConvEps ? v : 0.0f;
+    });
+    if (on) {
+        f2 *dst = fdl + ((size_t)st * n_part + head) * kFftM;
+#pragma unroll
+        for (int m = 0; m < 4; m++) dst[i + 64 * m] = s.b[sub][i + 64 * m];
+    }
+    __syncthreads();  // every read of prev is done
+    if (on) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const float v = nw[i + 64 * m];
+            prev[(size_t)st * kB + i + 64 * m] = fabsf(v) > kConvEps ? v : 0.0f;
+        }
+    }
+}
+
+constexpr int kCmacTy = 4;
+
+// partial[s][split] = sum over the split's partitions of fdl[s][(head - p) mod P] * H[s][p].
+// grid (n_split, S), block (128, kCmacTy).  This is the HBM-bound kernel.
+__global__ void __launch_bounds__(128 * kCmacTy) stream_cmac_kernel(const float4 *__restrict__ fdl, const float4 *__restrict__ H,
+                                                                     float4 *__restrict__ partial, int n_part, int per_split,
+                                                                     int head) {
+    __shared__ float4 red[kCmacTy][128];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int st = blockIdx.y, split = blockIdx.x;
+    const int p0 = split * per_split;
+    const int p1 = min(p0 + per_split, n_part);
+    const float4 *fs = fdl + (size_t)st * n_part * 128 + tx;
+    const float4 *hs = H + (size_t)st * n_part * 128 + tx;
+    Acc4 s = {0.f, 0.f, 0.f, 0.f, 0.f};
+    int p = p0 + ty;
+    for (; p + 3 * kCmacTy < p1; p += 4 * kCmacTy) {
+        float4 x[4], h[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int pp = p + u * kCmacTy;
+            int slot = head - pp;
+            if (slot < 0) slot += n_part;
+            x[u] = __ldcs(fs + (size_t)slot * 128);
+            h[u] = __ldcs(hs + (size_t)pp * 128);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) cmac4(s, x[u], h[u]);
+    }
+    for (; p < p1; p += kCmacTy) {
+        int slot = head - p;
+        if (slot < 0) slot += n_part;
+        cmac4(s, __ldcs(fs + (size_t)slot * 128), __ldcs(hs + (size_t)p * 128));
+    }
+    red[ty][tx] = finish4(s, tx == 0);
+    __syncthreads();
+    if (ty == 0) {
+        float4 r = red[0][tx];
+#pragma unroll
+        for (int k = 1; k < kCmacTy; k++) {
+            const float4 v = red[k][tx];
+            r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+        }
+        partial[((size_t)st * gridDim.x + split) * 128 + tx] = r;
+    }
+}
+
+// out[s] = last B samples of irfft(sum over splits of partial[s][split]) * (1/M)
+__global__ void __launch_bounds__(64 * kSub) stream_output_kernel(const f2 *__restrict__ partial, int n_split, float *__restrict__ out,
+                                                                   int n_streams) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int st = blockIdx.x * kSub + sub;
+    load_tables(s);
+    const bool on = st < n_streams;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        f2 acc = f2{0.f, 0.f};
+        if (on) {
+            const f2 *src = partial + (size_t)st * n_split * kFftM + i + 64 * m;
+            for (int q = 0; q < n_split; q++) acc = cadd(acc, src[(size_t)q * kFftM]);
+        }
+        s.b[sub][i + 64 * m] = acc;
+    }
+    __syncthreads();
+    irfft512_from_b(s, sub, i);
+    if (on) {
+        const float scale = 1.0f / (float)kFftM;
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const int n = 128 + i + 64 * m;
+            const f2 v = s.a[sub][n];
+            float2 *o = reinterpret_cast<float2 *>(out + (size_t)st * kB + 2 * (n - 128));
+            *o = make_float2(v.x * scale, v.y * scale);
+        }
+    }
+}
+
+inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace
+
+void conv_init_tables() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return;
+    f2 tw[kFftM], tw2[kFftM / 2 + 1];
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k < kFftM; k++) tw[k] = f2{(float)cos(two_pi * k / kFftM), (float)-sin(two_pi * k / kFftM)};
+    for (int k = 0; k <= kFftM / 2; k++)
+        tw2[k] = f2{(float)cos(two_pi * k / (2 * kFftM)), (float)-sin(two_pi * k / (2 * kFftM))};
+    cudaMemcpyToSymbol(g_tw, tw, sizeof tw);
+    cudaMemcpyToSymbol(g_tw2, tw2, sizeof tw2);
+    if (dev >= 0 && dev < 64) done[dev] = true;
+}
+
+cudaError_t launch_fixed_to_float(const long long *hist, float *out, long long n, float scale, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    fixed_to_float_kernel<<<min(blocks_for(n, 256), 4096), 256, 0, s>>>(hist, out, n, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_float_to_fixed(const float *in, long long *hist, long long n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    float_to_fixed_kernel<<<min(blocks_for(n, 256), 4096), 256, 0, s>>>(in, hist, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ir_spectra(const float *ir_f, int ir_len, float2 *H, int n_part, int block, cudaStream_t s) {
+    if (block != kB) return cudaErrorInvalidValue;
+    if (n_part <= 0) return cudaSuccess;
+    ir_spectra_kernel<<<blocks_for(n_part, kSub), 64 * kSub, 0, s>>>(ir_f, ir_len, reinterpret_cast<f2 *>(H), n_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_input_spectra(const float *x, int x_len, float2 *X, int n_xwin, int block, cudaStream_t s) {
+    if (block != kB) return cudaErrorInvalidValue;
+    if (n_xwin <= 0) return cudaSuccess;
+    input_spectra_kernel<<<blocks_for(n_xwin, kSub), 64 * kSub, 0, s>>>(x, x_len, reinterpret_cast<f2 *>(X), n_xwin);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_cmac(const float2 *X, int n_xwin, const float2 *H, int n_part, float2 *Y, int n_out_blocks,
+                              int block, cudaStream_t s) {
+    if (block != kB) return cudaErrorInvalidValue;
+    if (n_out_blocks <= 0) return cudaSuccess;
+    block_cmac_kernel<<<n_out_blocks, 128, 0, s>>>(reinterpret_cast<const float4 *>(X), n_xwin,
+                                                   reinterpret_cast<const float4 *>(H), n_part, reinterpret_cast<float4 *>(Y));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_output_blocks(const float2 *Y, int n_out_blocks, float *out, int out_len, float scale, int block,
+                                 cudaStream_t s) {
+    if (block != kB) return cudaErrorInvalidValue;
+    if (n_out_blocks <= 0) return cudaSuccess;
+    output_blocks_kernel<<<blocks_for(n_out_blocks, kSub), 64 * kSub, 0, s>>>(reinterpret_cast<const f2 *>(Y), n_out_blocks, out,
+                                                                              out_len, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_step(const StreamConv &c, const float *d_in, float *d_out, cudaStream_t s, int *launches) {
+    if (c.block != kB) return cudaErrorInvalidValue;
+    stream_input_kernel<<<blocks_for(c.n_streams, kSub), 64 * kSub, 0, s>>>(d_in, c.prev, reinterpret_cast<f2 *>(c.fdl),
+                                                                           c.n_streams, c.n_part, c.head);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    stream_cmac_kernel<<<dim3(c.n_split, c.n_streams), dim3(128, kCmacTy), 0, s>>>(
+        reinterpret_cast<const float4 *>(c.fdl), reinterpret_cast<const float4 *>(c.H), reinterpret_cast<float4 *>(c.partial),
+        c.n_part, c.part_per_split, c.head);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    stream_output_kernel<<<blocks_for(c.n_streams, kSub), 64 * kSub, 0, s>>>(reinterpret_cast<const f2 *>(c.partial), c.n_split,
+                                                                            d_out, c.n_streams);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && launches) *launches += 3;
+    return e;
+}
+
+}  // namespace rar

@@ -1,0 +1,827 @@
+// rar2d_api.cu -- the C-ABI of include/rar2d.h: contexts, wall upload, IR slots, trace and convolution
+// entry points.  Host-side bookkeeping only; all compute is in trace_kernel.cu and conv_kernels.cu.
+// There is no CPU path here: every compute entry point needs a CUDA device and fails otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rar_internal.h"
+#include "rar_layout.h"
+
+using namespace rar;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kMaxSlots = 1 << 16;
+constexpr int kBlock = 256;
+
+struct Slot {
+    long long *d_hist = nullptr;
+    long long cap_words = 0;
+    int impulse_length = 0;
+    int bands = 0;
+    bool configured = false;
+    // cached spectra of the slot's IR partitions (one-shot convolution)
+    float2 *d_H = nullptr;
+    int H_cap = 0;  // partitions allocated
+    int H_parts = 0;
+    bool H_valid = false;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Ticket {
+    bool active = false;
+    bool failed = false;
+    int out_len = 0;
+    cudaEvent_t done = nullptr;
+    PinnedBuf<float> h_in, h_out;
+    DevBuf<float> d_x, d_out;
+    DevBuf<float2> d_X, d_Y;
+};
+
+}  // namespace
+
+struct rar_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    DeviceFacts dev{};
+    std::string err;
+    long long launches = 0;
+
+    // walls
+    DevBuf<f4> d_geo, d_mat0;
+    DevBuf<f2> d_mat1;
+    DevBuf<float> d_band_abs;
+    int n_walls = -1;  // -1: never set
+    int band_rows = 0, band_count = 0;
+    std::vector<f4> h_geo, h_mat0;
+    std::vector<f2> h_mat1;
+
+    std::vector<Slot> slots;
+    DevBuf<unsigned long long> d_counters;  // 5 counters + 1 hit count
+    DevBuf<f4> d_debug;
+    int debug_entries = 0;
+    DevBuf<float> d_irf;  // float view of a slot (scratch)
+    std::vector<Ticket *> tickets;
+    std::vector<rar_convolver *> convolvers;
+};
+
+struct rar_convolver {
+    rar_context *ctx = nullptr;
+    StreamConv c{};
+    int max_ir_len = 0;
+    DevBuf<float2> H, fdl, partial;
+    DevBuf<float> prev, d_in, d_out, d_irf;
+    PinnedBuf<float> h_ir;
+};
+
+namespace {
+
+int fail(rar_context *ctx, int code, const char *fmt, const char *detail = "") {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, detail);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define RAR_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            std::string m__ = std::string(#call) + ": " + cudaGetErrorString(e__);       \
+            cudaGetLastError();                                                          \
+            return fail((ctx), e__ == cudaErrorMemoryAllocation ? RAR_ERR_NOMEM : RAR_ERR_CUDA, "%s", m__.c_str()); \
+        }                                                                                \
+    } while (0)
+
+#define RAR_ENTER(ctx)                                                        \
+    do {                                                                      \
+        if (!(ctx)) return fail(nullptr, RAR_ERR_INVALID, "null context");    \
+        cudaError_t e0__ = cudaSetDevice((ctx)->device);                      \
+        if (e0__ != cudaSuccess) return fail((ctx), RAR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e0__)); \
+    } while (0)
+
+Slot *get_slot(rar_context *ctx, int slot, bool create) {
+    if (slot < 0 || slot >= kMaxSlots) return nullptr;
+    if ((size_t)slot >= ctx->slots.size()) {
+        if (!create) return nullptr;
+        ctx->slots.resize(slot + 1);
+    }
+    return &ctx->slots[slot];
+}
+
+int check_trace_params(rar_context *ctx, const rar_trace_params *p) {
+    if (!p) return fail(ctx, RAR_ERR_INVALID, "null params");
+    if (ctx->n_walls < 0) return fail(ctx, RAR_ERR_STATE, "rar_set_walls has not been called");
+    if (p->ray_count <= 0) return fail(ctx, RAR_ERR_INVALID, "ray_count must be positive");
+    if (p->max_bounce_count < 0) return fail(ctx, RAR_ERR_INVALID, "max_bounce_count must be >= 0");
+    if (p->bands != 1 && p->bands != 8) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 1 or 8");
+    if (p->bands > 1 && (ctx->band_count != p->bands || ctx->band_rows != ctx->n_walls))
+        return fail(ctx, RAR_ERR_STATE, "banded trace needs rar_set_wall_band_absorption for the current walls");
+    if (p->impulse_length < 0 || p->sample_rate <= 0) return fail(ctx, RAR_ERR_INVALID, "bad impulse_length/sample_rate");
+    if (!(p->time_divisor > 0.0f)) return fail(ctx, RAR_ERR_INVALID, "time_divisor must be positive");
+    if (p->ray_begin < 0 || p->ray_end < p->ray_begin || p->ray_end > 0xffffffffLL)
+        return fail(ctx, RAR_ERR_INVALID, "bad ray range");
+    return RAR_OK;
+}
+
+void fill_launch(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
+    std::memset(&a, 0, sizeof a);
+    a.geo = ctx->d_geo.p;
+    a.mat0 = ctx->d_mat0.p;
+    a.mat1 = ctx->d_mat1.p;
+    a.band_abs = p->bands > 1 ? ctx->d_band_abs.p : nullptr;
+    a.n_walls = ctx->n_walls;
+    a.bands = p->bands;
+    a.p = ray_consts(*p);
+    ray_range(*p, a.ray_begin, a.ray_end);
+}
+
+Ticket *get_ticket(rar_context *ctx, int id) {
+    if (id < 0 || (size_t)id >= ctx->tickets.size()) return nullptr;
+    return ctx->tickets[id];
+}
+
+void free_ticket(Ticket *t) {
+    if (!t) return;
+    if (t->done) cudaEventDestroy(t->done);
+    t->h_in.release();
+    t->h_out.release();
+    t->d_x.release();
+    t->d_out.release();
+    t->d_X.release();
+    t->d_Y.release();
+    delete t;
+}
+
+// Makes the cached partition spectra of a slot current.
+int ensure_slot_spectra(rar_context *ctx, Slot &S) {
+    const int n_part = (S.impulse_length + kBlock - 1) / kBlock;
+    if (S.H_valid && S.H_parts == n_part) return RAR_OK;
+    if (n_part > S.H_cap) {
+        if (S.d_H) cudaFree(S.d_H);
+        S.d_H = nullptr;
+        S.H_cap = 0;
+        RAR_CUDA(ctx, cudaMalloc((void **)&S.d_H, (size_t)(n_part + 8) * kBlock * sizeof(float2)));
+        S.H_cap = n_part + 8;
+    }
+    RAR_CUDA(ctx, ctx->d_irf.reserve((size_t)S.impulse_length + 1));
+    RAR_CUDA(ctx, launch_fixed_to_float(S.d_hist, ctx->d_irf.p, S.impulse_length, 1.0f, ctx->stream));
+    RAR_CUDA(ctx, launch_ir_spectra(ctx->d_irf.p, S.impulse_length, S.d_H, n_part, kBlock, ctx->stream));
+    ctx->launches += 2;
+    S.H_parts = n_part;
+    S.H_valid = true;
+    return RAR_OK;
+}
+
+}  // namespace
+
+// ---- lifetime -------------------------------------------------------------------------------------
+
+extern "C" {
+
+int rar_version(void) { return RAR_VERSION; }
+
+int rar_create(int device, rar_context **out) {
+    if (!out) return fail(nullptr, RAR_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RAR_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n_dev) return fail(nullptr, RAR_ERR_INVALID, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, RAR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, RAR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, RAR_ERR_UNSUPPORTED, "%s", "device is not sm_100-class; this library ships sm_100a code only");
+    rar_context *ctx = new (std::nothrow) rar_context();
+    if (!ctx) return fail(nullptr, RAR_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->dev.sm_count = prop.multiProcessorCount;
+    ctx->dev.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    ctx->dev.sm_clock_khz = khz;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RAR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->slots.resize(2);  // ping / pong, RayTraceManager.cs:36
+    conv_init_tables();
+    e = ctx->d_counters.reserve(8);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return fail(nullptr, RAR_ERR_CUDA, "counter allocation: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return RAR_OK;
+}
+
+int rar_conv_destroy(rar_convolver *conv);
+
+int rar_destroy(rar_context *ctx) {
+    if (!ctx) return RAR_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    while (!ctx->convolvers.empty()) rar_conv_destroy(ctx->convolvers.back());
+    for (Ticket *t : ctx->tickets) free_ticket(t);
+    for (Slot &s : ctx->slots) {
+        if (s.d_hist) cudaFree(s.d_hist);
+        if (s.d_H) cudaFree(s.d_H);
+    }
+    ctx->d_geo.release();
+    ctx->d_mat0.release();
+    ctx->d_mat1.release();
+    ctx->d_band_abs.release();
+    ctx->d_counters.release();
+    ctx->d_debug.release();
+    ctx->d_irf.release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return RAR_OK;
+}
+
+const char *rar_last_error(const rar_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rar_set_stream(rar_context *ctx, void *cuda_stream) {
+    RAR_ENTER(ctx);
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RAR_OK;
+}
+
+int rar_sync(rar_context *ctx) {
+    RAR_ENTER(ctx);
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RAR_OK;
+}
+
+// ---- geometry ---------------------------------------------------------------------------------------
+
+int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
+    RAR_ENTER(ctx);
+    if (n < 0 || (n > 0 && !segments)) return fail(ctx, RAR_ERR_INVALID, "bad wall array");
+    static_assert(sizeof(rar_segment) == 40, "Segment must be 40 bytes (Helpers/SceneHelper.cs:15-22)");
+    static_assert(sizeof(rar_ray_info) == 16, "RayInfo must be 16 bytes (RayTraceManager.cs:43)");
+    const size_t pad = (size_t)n + 2;  // mat1 plane is bulk-copied in 16-byte units
+    ctx->h_geo.assign(pad, f4{0, 0, 0, 0});
+    ctx->h_mat0.assign(pad, f4{0, 0, 0, 0});
+    ctx->h_mat1.assign(pad, f2{0, 0});
+    split_walls(segments, n, ctx->h_geo.data(), ctx->h_mat0.data(), ctx->h_mat1.data());
+    RAR_CUDA(ctx, ctx->d_geo.reserve(pad));
+    RAR_CUDA(ctx, ctx->d_mat0.reserve(pad));
+    RAR_CUDA(ctx, ctx->d_mat1.reserve(pad));
+    // The previous planes may still be read by an enqueued trace; stream order makes the copy safe.
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_geo.p, ctx->h_geo.data(), pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat0.p, ctx->h_mat0.data(), pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat1.p, ctx->h_mat1.data(), pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors are pageable: finish before returning
+    if (n != ctx->n_walls) {
+        ctx->band_rows = 0;
+        ctx->band_count = 0;
+    }
+    ctx->n_walls = n;
+    return RAR_OK;
+}
+
+int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int32_t n, int32_t bands) {
+    RAR_ENTER(ctx);
+    if (ctx->n_walls < 0) return fail(ctx, RAR_ERR_STATE, "rar_set_walls has not been called");
+    if (n != ctx->n_walls) return fail(ctx, RAR_ERR_INVALID, "row count must equal the wall count");
+    if (bands != 8) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 8");
+    if (n > 0 && !absorption) return fail(ctx, RAR_ERR_INVALID, "null absorption table");
+    RAR_CUDA(ctx, ctx->d_band_abs.reserve((size_t)n * bands + 1));
+    if (n > 0)
+        RAR_CUDA(ctx, cudaMemcpy(ctx->d_band_abs.p, absorption, (size_t)n * bands * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->band_rows = n;
+    ctx->band_count = bands;
+    return RAR_OK;
+}
+
+// ---- IR slots ---------------------------------------------------------------------------------------
+
+int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length, int32_t bands) {
+    RAR_ENTER(ctx);
+    Slot *S = get_slot(ctx, slot, true);
+    if (!S) return fail(ctx, RAR_ERR_INVALID, "slot index out of range");
+    if (impulse_length < 0 || bands < 1) return fail(ctx, RAR_ERR_INVALID, "bad impulse_length/bands");
+    const long long words = (long long)impulse_length * bands;
+    if (words > S->cap_words) {
+        if (S->d_hist) {
+            RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(S->d_hist);
+            S->d_hist = nullptr;
+            S->cap_words = 0;
+        }
+        RAR_CUDA(ctx, cudaMalloc((void **)&S->d_hist, (size_t)(words + 16) * sizeof(long long)));
+        S->cap_words = words + 16;
+    }
+    if (words > 0) RAR_CUDA(ctx, cudaMemsetAsync(S->d_hist, 0, (size_t)words * sizeof(long long), ctx->stream));
+    S->impulse_length = impulse_length;
+    S->bands = bands;
+    S->configured = true;
+    S->H_valid = false;
+    return RAR_OK;
+}
+
+int rar_ir_read_fixed(rar_context *ctx, int32_t slot, int64_t *out, int64_t n) {
+    RAR_ENTER(ctx);
+    Slot *S = get_slot(ctx, slot, false);
+    if (!out || n < 0) return fail(ctx, RAR_ERR_INVALID, "bad output array");
+    const long long words = (S && S->configured) ? (long long)S->impulse_length * S->bands : 0;
+    // An unconfigured slot reads as zeros ("contents defined at creation").
+    const long long have = n < words ? n : words;
+    if (have > 0)
+        RAR_CUDA(ctx, cudaMemcpyAsync(out, S->d_hist, (size_t)have * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > have) std::memset(out + have, 0, (size_t)(n - have) * sizeof(int64_t));
+    return RAR_OK;
+}
+
+int rar_ir_read(rar_context *ctx, int32_t slot, float *out, int64_t n) {
+    RAR_ENTER(ctx);
+    Slot *S = get_slot(ctx, slot, false);
+    if (!out || n < 0) return fail(ctx, RAR_ERR_INVALID, "bad output array");
+    const long long words = (S && S->configured) ? (long long)S->impulse_length * S->bands : 0;
+    const long long have = n < words ? n : words;
+    if (have > 0) {
+        RAR_CUDA(ctx, ctx->d_irf.reserve((size_t)have));
+        RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, ctx->d_irf.p, have, 1.0f, ctx->stream));
+        ctx->launches++;
+        RAR_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_irf.p, (size_t)have * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > have) std::memset(out + have, 0, (size_t)(n - have) * sizeof(float));
+    return RAR_OK;
+}
+
+int rar_ir_write(rar_context *ctx, int32_t slot, const float *ir, int32_t impulse_length, int32_t bands) {
+    RAR_ENTER(ctx);
+    if (!ir && impulse_length > 0) return fail(ctx, RAR_ERR_INVALID, "null ir");
+    int rc = rar_ir_clear(ctx, slot, impulse_length, bands);
+    if (rc != RAR_OK) return rc;
+    Slot *S = get_slot(ctx, slot, false);
+    const long long words = (long long)impulse_length * bands;
+    if (words > 0) {
+        RAR_CUDA(ctx, ctx->d_irf.reserve((size_t)words));
+        RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_irf.p, ir, (size_t)words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        RAR_CUDA(ctx, launch_float_to_fixed(ctx->d_irf.p, S->d_hist, words, ctx->stream));
+        ctx->launches++;
+        RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return RAR_OK;
+}
+
+int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr, int64_t *n_words) {
+    RAR_ENTER(ctx);
+    Slot *S = get_slot(ctx, slot, false);
+    if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
+    if (device_ptr) *device_ptr = S->d_hist;
+    if (n_words) *n_words = (int64_t)S->impulse_length * S->bands;
+    S->H_valid = false;  // the caller may modify the histogram (all-reduce)
+    return RAR_OK;
+}
+
+// ---- trace ------------------------------------------------------------------------------------------
+
+int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) {
+    RAR_ENTER(ctx);
+    int rc = check_trace_params(ctx, params);
+    if (rc != RAR_OK) return rc;
+    Slot *S = get_slot(ctx, slot, false);
+    if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
+    if (S->impulse_length != params->impulse_length || S->bands != params->bands)
+        return fail(ctx, RAR_ERR_INVALID, "params impulse_length/bands do not match the slot");
+    TraceLaunch a;
+    fill_launch(ctx, params, a);
+    a.hist = reinterpret_cast<unsigned long long *>(S->d_hist);
+    const bool count = (params->flags & RAR_FLAG_COUNT_TESTS) != 0;
+    a.counters = count ? ctx->d_counters.p : nullptr;
+    if (params->debug_ray_count > 0) {
+        const int rows = params->debug_ray_count > 100 ? params->debug_ray_count : 100;
+        const long long entries = (long long)rows * (params->max_bounce_count + 1);
+        RAR_CUDA(ctx, ctx->d_debug.reserve((size_t)entries));
+        RAR_CUDA(ctx, cudaMemsetAsync(ctx->d_debug.p, 0, (size_t)entries * sizeof(f4), ctx->stream));
+        ctx->debug_entries = (int)entries;
+        a.debug_rays = ctx->d_debug.p;
+        a.debug_ray_count = params->debug_ray_count;
+        a.debug_capacity = (int)entries;
+    }
+    int launched = 0;
+    RAR_CUDA(ctx, launch_trace(a, count, ctx->dev, ctx->stream, &launched));
+    ctx->launches += launched;
+    S->H_valid = false;
+    return RAR_OK;
+}
+
+int rar_trace_hits(rar_context *ctx, const rar_trace_params *params, rar_ray_info *hits, rar_hit_key *keys,
+                   int64_t capacity, int64_t *count) {
+    RAR_ENTER(ctx);
+    int rc = check_trace_params(ctx, params);
+    if (rc != RAR_OK) return rc;
+    if (capacity < 0 || (capacity > 0 && !hits)) return fail(ctx, RAR_ERR_INVALID, "bad hit array");
+    DevBuf<rar_ray_info> d_hits;
+    DevBuf<rar_hit_key> d_keys;
+    RAR_CUDA(ctx, d_hits.reserve((size_t)capacity + 1));
+    if (keys) RAR_CUDA(ctx, d_keys.reserve((size_t)capacity + 1));
+    unsigned long long *d_count = ctx->d_counters.p + 5;
+    RAR_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
+    TraceLaunch a;
+    fill_launch(ctx, params, a);
+    a.hits = d_hits.p;
+    a.keys = keys ? d_keys.p : nullptr;
+    a.hit_cap = capacity;
+    a.hit_count = d_count;
+    const bool cnt = (params->flags & RAR_FLAG_COUNT_TESTS) != 0;
+    a.counters = cnt ? ctx->d_counters.p : nullptr;
+    int launched = 0;
+    cudaError_t e = launch_trace(a, cnt, ctx->dev, ctx->stream, &launched);
+    ctx->launches += launched;
+    unsigned long long produced = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&produced, d_count, sizeof produced, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    const long long stored = (long long)produced < capacity ? (long long)produced : capacity;
+    if (e == cudaSuccess && stored > 0) {
+        e = cudaMemcpy(hits, d_hits.p, (size_t)stored * sizeof(rar_ray_info), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && keys) e = cudaMemcpy(keys, d_keys.p, (size_t)stored * sizeof(rar_hit_key), cudaMemcpyDeviceToHost);
+    }
+    d_hits.release();
+    d_keys.release();
+    RAR_CUDA(ctx, e);
+    if (count) *count = (int64_t)produced;
+    return RAR_OK;
+}
+
+int rar_get_counters(rar_context *ctx, rar_counters *out, int32_t reset) {
+    RAR_ENTER(ctx);
+    if (!out) return fail(ctx, RAR_ERR_INVALID, "null out");
+    unsigned long long v[5];
+    RAR_CUDA(ctx, cudaMemcpyAsync(v, ctx->d_counters.p, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) RAR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof v, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->ray_bounces = v[0];
+    out->nearest_tests = v[1];
+    out->shadow_tests = v[2];
+    out->direct_hits = v[3];
+    out->nee_hits = v[4];
+    return RAR_OK;
+}
+
+int rar_get_debug_rays(rar_context *ctx, float *out_xyzw, int64_t n_float4) {
+    RAR_ENTER(ctx);
+    if (!out_xyzw || n_float4 < 0) return fail(ctx, RAR_ERR_INVALID, "bad output array");
+    const long long have = n_float4 < ctx->debug_entries ? n_float4 : ctx->debug_entries;
+    if (have > 0)
+        RAR_CUDA(ctx, cudaMemcpyAsync(out_xyzw, ctx->d_debug.p, (size_t)have * sizeof(f4), cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_float4 > have) std::memset(out_xyzw + have * 4, 0, (size_t)(n_float4 - have) * sizeof(f4));
+    return RAR_OK;
+}
+
+// ---- one-shot convolution ---------------------------------------------------------------------------
+
+int rar_convolve_begin(rar_context *ctx, int32_t slot, const float *in, int32_t in_len, int32_t accum_count,
+                       int32_t *ticket) {
+    RAR_ENTER(ctx);
+    if (!ticket) return fail(ctx, RAR_ERR_INVALID, "null ticket");
+    *ticket = -1;
+    if (in_len < 0 || (in_len > 0 && !in)) return fail(ctx, RAR_ERR_INVALID, "bad input array");
+    Slot *S = get_slot(ctx, slot, false);
+    if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
+    if (S->bands != 1) return fail(ctx, RAR_ERR_UNSUPPORTED, "convolution needs a broadband (bands == 1) slot");
+    const int ir_len = S->impulse_length;
+    const int out_len = in_len + ir_len;  // AudioConvolve.compute:15
+
+    int id = -1;
+    for (size_t i = 0; i < ctx->tickets.size(); i++)
+        if (!ctx->tickets[i]->active) { id = (int)i; break; }
+    if (id < 0) {
+        Ticket *t = new (std::nothrow) Ticket();
+        if (!t) return fail(ctx, RAR_ERR_NOMEM, "out of host memory");
+        if (cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming) != cudaSuccess) {
+            delete t;
+            return fail(ctx, RAR_ERR_CUDA, "cudaEventCreate failed");
+        }
+        ctx->tickets.push_back(t);
+        id = (int)ctx->tickets.size() - 1;
+    }
+    Ticket &T = *ctx->tickets[id];
+    T.out_len = out_len;
+    T.failed = false;
+    RAR_CUDA(ctx, T.h_out.reserve((size_t)out_len + 1));
+    RAR_CUDA(ctx, T.d_out.reserve((size_t)out_len + 1));
+
+    const bool zero = accum_count <= 0 || in_len == 0 || ir_len == 0;  // AudioConvolve.compute:30
+    if (zero) {
+        if (out_len > 0) RAR_CUDA(ctx, cudaMemsetAsync(T.d_out.p, 0, (size_t)out_len * sizeof(float), ctx->stream));
+    } else {
+        int rc = ensure_slot_spectra(ctx, *S);
+        if (rc != RAR_OK) return rc;
+        const int n_part = S->H_parts;
+        const int n_xwin = (in_len + kBlock - 1) / kBlock + 1;
+        const int n_out_blocks = (out_len + kBlock - 1) / kBlock;
+        RAR_CUDA(ctx, T.h_in.reserve((size_t)in_len));
+        RAR_CUDA(ctx, T.d_x.reserve((size_t)in_len));
+        RAR_CUDA(ctx, T.d_X.reserve((size_t)n_xwin * kBlock));
+        RAR_CUDA(ctx, T.d_Y.reserve((size_t)n_out_blocks * kBlock));
+        std::memcpy(T.h_in.p, in, (size_t)in_len * sizeof(float));
+        RAR_CUDA(ctx, cudaMemcpyAsync(T.d_x.p, T.h_in.p, (size_t)in_len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        RAR_CUDA(ctx, launch_input_spectra(T.d_x.p, in_len, T.d_X.p, n_xwin, kBlock, ctx->stream));
+        RAR_CUDA(ctx, launch_block_cmac(T.d_X.p, n_xwin, S->d_H, n_part, T.d_Y.p, n_out_blocks, kBlock, ctx->stream));
+        const float scale = (1.0f / (float)accum_count) / (float)kBlock;
+        RAR_CUDA(ctx, launch_output_blocks(T.d_Y.p, n_out_blocks, T.d_out.p, out_len, scale, kBlock, ctx->stream));
+        ctx->launches += 3;
+    }
+    if (out_len > 0)
+        RAR_CUDA(ctx, cudaMemcpyAsync(T.h_out.p, T.d_out.p, (size_t)out_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaEventRecord(T.done, ctx->stream));
+    T.active = true;
+    *ticket = id;
+    return RAR_OK;
+}
+
+int rar_poll(rar_context *ctx, int32_t ticket) {
+    RAR_ENTER(ctx);
+    Ticket *T = get_ticket(ctx, ticket);
+    if (!T || !T->active) return fail(ctx, RAR_ERR_INVALID, "unknown ticket");
+    cudaError_t e = cudaEventQuery(T->done);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) {
+        cudaGetLastError();
+        return 0;
+    }
+    T->failed = true;
+    return fail(ctx, RAR_ERR_CUDA, "ticket failed: %s", cudaGetErrorString(e));
+}
+
+int rar_convolve_end(rar_context *ctx, int32_t ticket, float *out, int32_t out_len) {
+    RAR_ENTER(ctx);
+    Ticket *T = get_ticket(ctx, ticket);
+    if (!T || !T->active) return fail(ctx, RAR_ERR_INVALID, "unknown ticket");
+    if (out_len < 0 || (out_len > 0 && !out)) return fail(ctx, RAR_ERR_INVALID, "bad output array");
+    cudaError_t e = cudaEventSynchronize(T->done);
+    T->active = false;
+    RAR_CUDA(ctx, e);
+    const int n = out_len < T->out_len ? out_len : T->out_len;
+    if (n > 0) std::memcpy(out, T->h_out.p, (size_t)n * sizeof(float));
+    if (out_len > n) std::memset(out + n, 0, (size_t)(out_len - n) * sizeof(float));
+    return RAR_OK;
+}
+
+int rar_convolve(rar_context *ctx, int32_t slot, const float *in, int32_t in_len, int32_t accum_count, float *out,
+                 int32_t out_len) {
+    int32_t ticket = -1;
+    int rc = rar_convolve_begin(ctx, slot, in, in_len, accum_count, &ticket);
+    if (rc != RAR_OK) return rc;
+    return rar_convolve_end(ctx, ticket, out, out_len);
+}
+
+// ---- streaming convolver ----------------------------------------------------------------------------
+
+int rar_conv_create(rar_context *ctx, int32_t n_streams, int32_t block, int32_t max_ir_len, rar_convolver **out) {
+    RAR_ENTER(ctx);
+    if (!out) return fail(ctx, RAR_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (n_streams <= 0 || max_ir_len <= 0) return fail(ctx, RAR_ERR_INVALID, "n_streams and max_ir_len must be positive");
+    if (block != kBlock) return fail(ctx, RAR_ERR_UNSUPPORTED, "block must be 256");
+    rar_convolver *cv = new (std::nothrow) rar_convolver();
+    if (!cv) return fail(ctx, RAR_ERR_NOMEM, "out of host memory");
+    cv->ctx = ctx;
+    cv->max_ir_len = max_ir_len;
+    StreamConv &c = cv->c;
+    c.n_streams = n_streams;
+    c.block = block;
+    c.n_part = (max_ir_len + block - 1) / block;
+    // Split the partitions of a stream over several CTAs so that the grid is many waves deep.
+    int want = (32 * ctx->dev.sm_count + n_streams - 1) / n_streams;
+    int max_split = (c.n_part + 15) / 16;
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    c.part_per_split = (c.n_part + want - 1) / want;
+    c.n_split = (c.n_part + c.part_per_split - 1) / c.part_per_split;
+    c.head = 0;
+    const size_t spec = (size_t)n_streams * c.n_part * block;
+    cudaError_t e = cv->H.reserve(spec);
+    if (e == cudaSuccess) e = cv->fdl.reserve(spec);
+    if (e == cudaSuccess) e = cv->partial.reserve((size_t)n_streams * c.n_split * block);
+    if (e == cudaSuccess) e = cv->prev.reserve((size_t)n_streams * block);
+    if (e == cudaSuccess) e = cv->d_in.reserve((size_t)n_streams * block);
+    if (e == cudaSuccess) e = cv->d_out.reserve((size_t)n_streams * block);
+    if (e == cudaSuccess) e = cv->d_irf.reserve((size_t)c.n_part * block);
+    if (e == cudaSuccess) e = cv->h_ir.reserve((size_t)c.n_part * block);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cv->H.p, 0, spec * sizeof(float2), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cv->fdl.p, 0, spec * sizeof(float2), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cv->prev.p, 0, (size_t)n_streams * block * sizeof(float), ctx->stream);
+    if (e != cudaSuccess) {
+        cv->H.release(); cv->fdl.release(); cv->partial.release(); cv->prev.release();
+        cv->d_in.release(); cv->d_out.release(); cv->d_irf.release(); cv->h_ir.release();
+        delete cv;
+        RAR_CUDA(ctx, e);
+    }
+    c.H = cv->H.p;
+    c.fdl = cv->fdl.p;
+    c.partial = cv->partial.p;
+    c.prev = cv->prev.p;
+    ctx->convolvers.push_back(cv);
+    *out = cv;
+    return RAR_OK;
+}
+
+int rar_conv_destroy(rar_convolver *cv) {
+    if (!cv) return RAR_OK;
+    rar_context *ctx = cv->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < ctx->convolvers.size(); i++)
+        if (ctx->convolvers[i] == cv) {
+            ctx->convolvers.erase(ctx->convolvers.begin() + i);
+            break;
+        }
+    cv->H.release(); cv->fdl.release(); cv->partial.release(); cv->prev.release();
+    cv->d_in.release(); cv->d_out.release(); cv->d_irf.release(); cv->h_ir.release();
+    delete cv;
+    return RAR_OK;
+}
+
+int rar_conv_set_ir(rar_convolver *cv, int32_t stream, const float *ir, int32_t ir_len, float scale) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    if (stream < 0 || stream >= cv->c.n_streams) return fail(ctx, RAR_ERR_INVALID, "stream index out of range");
+    if (ir_len < 0 || ir_len > cv->max_ir_len || (ir_len > 0 && !ir)) return fail(ctx, RAR_ERR_INVALID, "bad ir array");
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h_ir is reused between calls
+    for (int i = 0; i < ir_len; i++) cv->h_ir.p[i] = ir[i] * scale;
+    if (ir_len > 0)
+        RAR_CUDA(ctx, cudaMemcpyAsync(cv->d_irf.p, cv->h_ir.p, (size_t)ir_len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    float2 *H = cv->c.H + (size_t)stream * cv->c.n_part * cv->c.block;
+    RAR_CUDA(ctx, launch_ir_spectra(cv->d_irf.p, ir_len, H, cv->c.n_part, cv->c.block, ctx->stream));
+    ctx->launches++;
+    return RAR_OK;
+}
+
+int rar_conv_set_ir_from_slot(rar_convolver *cv, int32_t stream, int32_t slot, int32_t accum_count) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    if (stream < 0 || stream >= cv->c.n_streams) return fail(ctx, RAR_ERR_INVALID, "stream index out of range");
+    Slot *S = get_slot(ctx, slot, false);
+    if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured");
+    if (S->bands != 1) return fail(ctx, RAR_ERR_UNSUPPORTED, "convolution needs a broadband (bands == 1) slot");
+    if (S->impulse_length > cv->max_ir_len) return fail(ctx, RAR_ERR_INVALID, "slot IR is longer than max_ir_len");
+    const float scale = accum_count > 0 ? 1.0f / (float)accum_count : 0.0f;
+    RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, cv->d_irf.p, S->impulse_length, scale, ctx->stream));
+    float2 *H = cv->c.H + (size_t)stream * cv->c.n_part * cv->c.block;
+    RAR_CUDA(ctx, launch_ir_spectra(cv->d_irf.p, S->impulse_length, H, cv->c.n_part, cv->c.block, ctx->stream));
+    ctx->launches += 2;
+    return RAR_OK;
+}
+
+int rar_conv_reset(rar_convolver *cv) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    const size_t spec = (size_t)cv->c.n_streams * cv->c.n_part * cv->c.block;
+    RAR_CUDA(ctx, cudaMemsetAsync(cv->fdl.p, 0, spec * sizeof(float2), ctx->stream));
+    RAR_CUDA(ctx, cudaMemsetAsync(cv->prev.p, 0, (size_t)cv->c.n_streams * cv->c.block * sizeof(float), ctx->stream));
+    cv->c.head = 0;
+    return RAR_OK;
+}
+
+int rar_conv_process_device(rar_convolver *cv, const float *d_in, float *d_out) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    if (!d_in || !d_out) return fail(ctx, RAR_ERR_INVALID, "null device array");
+    int launched = 0;
+    RAR_CUDA(ctx, launch_stream_step(cv->c, d_in, d_out, ctx->stream, &launched));
+    ctx->launches += launched;
+    cv->c.head = (cv->c.head + 1) % cv->c.n_part;
+    return RAR_OK;
+}
+
+int rar_conv_process(rar_convolver *cv, const float *in, float *out) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    if (!in || !out) return fail(ctx, RAR_ERR_INVALID, "null array");
+    const size_t bytes = (size_t)cv->c.n_streams * cv->c.block * sizeof(float);
+    RAR_CUDA(ctx, cudaMemcpyAsync(cv->d_in.p, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = rar_conv_process_device(cv, cv->d_in.p, cv->d_out.p);
+    if (rc != RAR_OK) return rc;
+    RAR_CUDA(ctx, cudaMemcpyAsync(out, cv->d_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RAR_OK;
+}
+
+int64_t rar_conv_bytes_per_block(const rar_convolver *cv) {
+    if (!cv) return 0;
+    const StreamConv &c = cv->c;
+    const int64_t row = (int64_t)c.block * sizeof(float2);
+    // per stream: P delay-line spectra + P IR spectra read, 1 spectrum written, partial sums written and
+    // read back, block in + block out + previous-block read/write.
+    const int64_t per_stream = 2 * (int64_t)c.n_part * row + row + 2 * (int64_t)c.n_split * row + 4 * (int64_t)c.block * 4;
+    return per_stream * c.n_streams;
+}
+
+// ---- measurement helpers ----------------------------------------------------------------------------
+
+int rar_device_info(rar_context *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int32_t *smem_optin_bytes) {
+    RAR_ENTER(ctx);
+    if (sm_count) *sm_count = ctx->dev.sm_count;
+    if (sm_clock_khz) *sm_clock_khz = ctx->dev.sm_clock_khz;
+    if (smem_optin_bytes) *smem_optin_bytes = ctx->dev.smem_optin;
+    return RAR_OK;
+}
+
+int rar_measure_fp32_peak(rar_context *ctx, double *lane_ops_per_s) {
+    RAR_ENTER(ctx);
+    if (!lane_ops_per_s) return fail(ctx, RAR_ERR_INVALID, "null out");
+    DevBuf<float> sink;
+    RAR_CUDA(ctx, sink.reserve(4));
+    const int blocks = ctx->dev.sm_count * 8, threads = 256, iters = 4000;
+    cudaEvent_t e0, e1;
+    RAR_CUDA(ctx, cudaEventCreate(&e0));
+    RAR_CUDA(ctx, cudaEventCreate(&e1));
+    cudaError_t e = launch_fp32_peak(sink.p, blocks, threads, iters / 4, ctx->stream);  // warm-up
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 3 && e == cudaSuccess; rep++) {
+        cudaEventRecord(e0, ctx->stream);
+        e = launch_fp32_peak(sink.p, blocks, threads, iters, ctx->stream);
+        cudaEventRecord(e1, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0 && ms < best_ms) best_ms = ms;
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    sink.release();
+    RAR_CUDA(ctx, e);
+    const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+    *lane_ops_per_s = ops / (best_ms * 1e-3);
+    return RAR_OK;
+}
+
+int64_t rar_launch_count(const rar_context *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// rar_internal.h -- launch descriptors shared by the kernel translation units and the C-ABI layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rar2d.h"
+#include "rar_ray.cuh"
+
+namespace rar {
+
+// Everything one launch of the trace kernel needs.  Passed by value as a __grid_constant__.
+struct TraceLaunch {
+    const f4 *geo;          // [n_walls] endpoint plane (TMA bulk-copy source, 16-byte records)
+    const f4 *mat0;         // [n_walls] normal + absorption + scattering
+    const f2 *mat1;         // [n_walls] transmission + ior
+    const float *band_abs;  // [n_walls][bands] or nullptr
+    int n_walls;
+    int bands;
+    RayConsts p;
+    long long ray_begin, ray_end;
+    unsigned long long *hist;  // [impulse_length][bands] Q23.40, nullptr in hit-list mode
+    rar_ray_info *hits;        // hit-list mode outputs
+    rar_hit_key *keys;
+    long long hit_cap;
+    unsigned long long *hit_count;
+    unsigned long long *counters;  // 5 words (rar_counters) or nullptr
+    f4 *debug_rays;                // max(100, debug_ray_count) * (max_bounce_count+1) or nullptr
+    int debug_ray_count;
+    int debug_capacity;            // entries in debug_rays
+};
+
+struct DeviceFacts {
+    int sm_count;
+    int smem_optin;  // bytes of dynamic shared memory a block may opt in to
+    int sm_clock_khz;
+};
+
+// trace_kernel.cu
+cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFacts &dev, cudaStream_t stream,
+                         int *launches);
+cudaError_t launch_fp32_peak(float *d_sink, int blocks, int threads, int iters, cudaStream_t stream);
+
+// conv_kernels.cu -- all spectra are "packed half spectra" of a real FFT of size 2*B: B complex values
+// per block, bin 0 holding (DC, Nyquist) in (re, im).
+struct ConvPlan {
+    int block;       // B (256)
+    int log2_block;  // 8
+};
+
+// hist (Q23.40 int64) -> float, optionally scaled; n values.
+cudaError_t launch_fixed_to_float(const long long *hist, float *out, long long n, float scale, cudaStream_t s);
+cudaError_t launch_float_to_fixed(const float *in, long long *hist, long long n, cudaStream_t s);
+
+// Spectra of the IR partitions: H[p] = rfft([ir[p*B .. p*B+B), 0...0]) for p in [0, n_part).
+// ir_f (float, already scaled) has ir_len valid samples.
+cudaError_t launch_ir_spectra(const float *ir_f, int ir_len, float2 *H, int n_part, int block, cudaStream_t s);
+
+// One-shot convolution (AudioConvolve semantics):
+//  X[j] = rfft([x[(j-1)B .. jB), x[jB .. (j+1)B)]) with |x| <= 1e-4 zeroed, j in [0, n_xwin)
+cudaError_t launch_input_spectra(const float *x, int x_len, float2 *X, int n_xwin, int block, cudaStream_t s);
+//  Y[j] = sum_p X[j-p] * H[p], j in [0, n_out_blocks)
+cudaError_t launch_block_cmac(const float2 *X, int n_xwin, const float2 *H, int n_part, float2 *Y, int n_out_blocks,
+                              int block, cudaStream_t s);
+//  out[jB + i] = irfft(Y[j])[B + i] * scale for jB+i < out_len; the rest of out (if any) is zeroed
+cudaError_t launch_output_blocks(const float2 *Y, int n_out_blocks, float *out, int out_len, float scale, int block,
+                                 cudaStream_t s);
+
+// Streaming convolver (one block per stream per call).
+struct StreamConv {
+    int n_streams, block, n_part, n_split, part_per_split;
+    float2 *H;        // [S][P][B]
+    float2 *fdl;      // [S][P][B] ring of input-window spectra
+    float2 *partial;  // [S][n_split][B]
+    float *prev;      // [S][B] previous input block (first half of the overlap-save window)
+    int head;         // ring slot the next window is written to
+};
+cudaError_t launch_stream_step(const StreamConv &c, const float *d_in, float *d_out, cudaStream_t s, int *launches);
+
+void conv_init_tables();  // uploads twiddle tables to constant memory of the current device (idempotent per device)
+
+}  // namespace rar

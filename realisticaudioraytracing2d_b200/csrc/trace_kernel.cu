@@ -1,0 +1,345 @@
+// trace_kernel.cu -- the fused Trace + ProcessHits kernel for sm_100a.
+//
+// Replaces Raytrace2D.compute `Trace` (:49-156) and `ProcessHits` (:157-165): one thread per ray,
+// looping over bounces; every arrival is added straight into the time-binned (optionally banded)
+// 64-bit fixed-point impulse-response histogram, so there is no hit buffer and no hit-count
+// round trip through the host (RayTraceManager.cs:208-209).
+//
+//  * The wall planes are staged into shared memory once per CTA by 1-D TMA bulk copies
+//    (cp.async.bulk.shared::cluster.global + mbarrier complete_tx; SASS: UBLKCP).  All lanes of a
+//    warp read the same wall record, so the inner loop is one broadcast LDS.128 per test.
+//  * CTAs are persistent: the grid is sized to the resident capacity of the device and each CTA
+//    strides over tiles of rays, so a 10k-wall scene (160 KB) is staged 148 times, not 65 536 times.
+//  * Deposits are warp-aggregated: lanes that hit the same bin are found with __match_any_sync, their
+//    Q23.40 values are summed with three __reduce_add_sync limb reductions, and one lane issues a single
+//    64-bit integer atomic.  Integer addition commutes, so the histogram is bit-identical for any
+//    scheduling, any grid and any number of GPUs.
+//
+// Compiled with --fmad=false: the arithmetic contract of rar_math.cuh fixes every rounding.
+#include <cuda_runtime.h>
+
+#include "rar_internal.h"
+
+namespace rar {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- TMA / mbarrier primitives (PTX ISA 8.x, sm_90+) ------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// ---- scene views ------------------------------------------------------------------------------------
+
+// STAGE 0: endpoint and material planes in shared memory; 1: endpoints in shared, materials in global;
+// 2: everything read through the read-only global path (scenes too large for shared memory).
+template <int STAGE>
+struct SceneView {
+    const f4 *g;
+    const f4 *m0;
+    const f2 *m1;
+    const float *ba;
+    int n, nb;
+    __device__ __forceinline__ int n_walls() const { return n; }
+    __device__ __forceinline__ f4 geo(int w) const {
+        if (STAGE == 2) {
+            float4 v = __ldg(reinterpret_cast<const float4 *>(g) + w);
+            return f4{v.x, v.y, v.z, v.w};
+        }
+        return g[w];
+    }
+    __device__ __forceinline__ f4 mat0(int w) const {
+        if (STAGE != 0) {
+            float4 v = __ldg(reinterpret_cast<const float4 *>(m0) + w);
+            return f4{v.x, v.y, v.z, v.w};
+        }
+        return m0[w];
+    }
+    __device__ __forceinline__ f2 mat1(int w) const {
+        if (STAGE != 0) {
+            float2 v = __ldg(reinterpret_cast<const float2 *>(m1) + w);
+            return f2{v.x, v.y};
+        }
+        return m1[w];
+    }
+    __device__ __forceinline__ const float *band_abs(int w) const { return ba + (size_t)w * nb; }
+};
+
+// ---- warp-aggregated fixed-point deposit ------------------------------------------------------------
+
+// Sum of q over the lanes in `peers` (all of which call this with the same mask).  64-bit values are
+// reduced as three limbs with the 32-bit REDUX instruction: 24 + 24 + 16 (signed) bits.
+__device__ __forceinline__ long long group_sum_q(unsigned peers, long long q) {
+    unsigned lo = (unsigned)(q & 0xffffff);
+    unsigned mid = (unsigned)((q >> 24) & 0xffffff);
+    int hi = (int)(q >> 48);
+    lo = __reduce_add_sync(peers, lo);
+    mid = __reduce_add_sync(peers, mid);
+    hi = __reduce_add_sync(peers, hi);
+    return (long long)lo + ((long long)mid << 24) + ((long long)hi << 48);
+}
+
+template <int BANDS>
+__device__ __forceinline__ void deposit_hist(const TraceLaunch &a, const Arrival<BANDS> &h, unsigned lane) {
+    int bin = -1;
+    if (h.has) bin = time_bin(h.t, a.p.sample_rate, a.p.time_divisor, a.p.impulse_length);
+    if (!__any_sync(kFull, bin >= 0)) return;
+    const unsigned peers = __match_any_sync(kFull, bin);
+    const bool valid = bin >= 0;
+    const bool shared_bin = valid && (peers & (peers - 1)) != 0;  // same for every lane of a peer group
+    const bool leader = valid && lane == (unsigned)(__ffs(peers) - 1);
+    if (BANDS == 1) {
+        long long q = valid ? quantize_energy(h.e) : 0;
+        if (shared_bin) q = group_sum_q(peers, q);
+        if (leader && q != 0) atomicAdd(a.hist + bin, (unsigned long long)q);
+    } else {
+        unsigned long long *row = a.hist + (size_t)(valid ? bin : 0) * BANDS;
+#pragma unroll
+        for (int b = 0; b < BANDS; b++) {
+            long long q = valid ? quantize_energy(h.band_e[b]) : 0;
+            if (shared_bin) q = group_sum_q(peers, q);
+            if (leader && q != 0) atomicAdd(row + b, (unsigned long long)q);
+        }
+    }
+}
+
+template <int BANDS>
+__device__ __forceinline__ void emit_hit(const TraceLaunch &a, const Arrival<BANDS> &h, uint32_t id, int bounce, int kind) {
+    if (!h.has) return;
+    unsigned long long slot = atomicAdd(a.hit_count, 1ull);
+    if ((long long)slot < a.hit_cap) {
+        a.hits[slot] = rar_ray_info{h.t, h.e, {h.hx, h.hy}};
+        if (a.keys) a.keys[slot] = rar_hit_key{id, (uint16_t)bounce, (uint16_t)kind};
+    }
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+
+template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT>
+__global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    f4 *s_geo = reinterpret_cast<f4 *>(smem_raw + 16);
+    f4 *s_mat0 = s_geo + a.n_walls;
+    f2 *s_mat1 = reinterpret_cast<f2 *>(s_mat0 + a.n_walls);
+
+    if (STAGE < 2 && a.n_walls > 0) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t geo_bytes = (uint32_t)a.n_walls * 16u;
+            const uint32_t m1_bytes = ((uint32_t)a.n_walls * 8u + 15u) & ~15u;  // planes are padded to 16 B
+            const uint32_t total = STAGE == 0 ? geo_bytes * 2u + m1_bytes : geo_bytes;
+            mbar_arrive_expect_tx(bar, total);
+            bulk_copy_g2s(s_geo, a.geo, geo_bytes, bar);
+            if (STAGE == 0) {
+                bulk_copy_g2s(s_mat0, a.mat0, geo_bytes, bar);
+                bulk_copy_g2s(s_mat1, a.mat1, m1_bytes, bar);
+            }
+        }
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
+
+    SceneView<STAGE> sc;
+    sc.g = STAGE < 2 ? s_geo : a.geo;
+    sc.m0 = STAGE == 0 ? s_mat0 : a.mat0;
+    sc.m1 = STAGE == 0 ? s_mat1 : a.mat1;
+    sc.ba = a.band_abs;
+    sc.n = a.n_walls;
+    sc.nb = a.bands;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const long long n_rays = a.ray_end - a.ray_begin;
+    const int max_b = a.p.max_bounce_count;
+    RayCounters ctr = {0, 0, 0, 0, 0};
+
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_rays; base += (long long)gridDim.x * blockDim.x) {
+        const long long idx = base + threadIdx.x;
+        bool alive = idx < n_rays;
+        const uint32_t id = (uint32_t)(a.ray_begin + idx);
+        RayState<BANDS> r;
+        if (alive) ray_init(r, id, a.p);
+
+        f4 *dbg = nullptr;
+        bool dbg100 = false, dbgN = false;
+        if (a.debug_rays != nullptr && alive) {
+            const long long row = (long long)id * (max_b + 1);
+            if (row + max_b < a.debug_capacity) {
+                dbg = a.debug_rays + row;
+                dbg100 = id < 100u;                          // Raytrace2D.compute:63,96 (hard-coded 100)
+                dbgN = id < (uint32_t)a.debug_ray_count;     // :87
+                if (dbg100) dbg[0] = f4{r.px, r.py, r.energy, 0.0f};
+            }
+        }
+
+        for (int i = 0; i < max_b; i++) {
+            if (!__any_sync(kFull, alive)) break;
+            Arrival<BANDS> direct, nee;
+            direct.has = 0;
+            nee.has = 0;
+            if (alive) {
+                alive = ray_bounce<BANDS, COUNT>(sc, a.p, r, direct, nee, &ctr, dbg100 ? dbg + i + 1 : nullptr,
+                                                 dbgN ? dbg + i + 1 : nullptr);
+            }
+            __syncwarp();
+            if (HITS) {
+                emit_hit(a, direct, id, i, 0);
+                emit_hit(a, nee, id, i, 1);
+            } else {
+                deposit_hist(a, direct, lane);
+                deposit_hist(a, nee, lane);
+            }
+        }
+    }
+
+    if (COUNT && a.counters != nullptr) {
+        unsigned long long v[5] = {ctr.ray_bounces, ctr.nearest_tests, ctr.shadow_tests, ctr.direct_hits, ctr.nee_hits};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            unsigned long long s = warp_sum_u64(v[k]);
+            if (lane == 0 && s != 0) atomicAdd(a.counters + k, s);
+        }
+    }
+}
+
+// Register-only FFMA loop: the FP32 issue peak the ray stage is measured against.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f;
+    float x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+    const float m = 0.999f, c = 1e-4f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = __fmaf_rn(x0, m, c); x1 = __fmaf_rn(x1, m, c); x2 = __fmaf_rn(x2, m, c); x3 = __fmaf_rn(x3, m, c);
+            x4 = __fmaf_rn(x4, m, c); x5 = __fmaf_rn(x5, m, c); x6 = __fmaf_rn(x6, m, c); x7 = __fmaf_rn(x7, m, c);
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678f) sink[0] = s;
+}
+
+// ---- launch selection -------------------------------------------------------------------------------
+
+struct KernelChoice {
+    const void *fn;
+    int max_threads;
+};
+
+template <int BANDS, bool COUNT, bool HITS, int STAGE>
+KernelChoice pick_maxt(bool big_block) {
+    if (big_block) return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, STAGE, 1024>, 1024};
+    return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, STAGE, 256>, 256};
+}
+template <int BANDS, bool COUNT, bool HITS>
+KernelChoice pick_stage(int stage, bool big) {
+    switch (stage) {
+        case 0: return pick_maxt<BANDS, COUNT, HITS, 0>(big);
+        case 1: return pick_maxt<BANDS, COUNT, HITS, 1>(big);
+        default: return pick_maxt<BANDS, COUNT, HITS, 2>(big);
+    }
+}
+template <int BANDS>
+KernelChoice pick_mode(bool count, bool hits, int stage, bool big) {
+    if (hits) return count ? pick_stage<BANDS, true, true>(stage, big) : pick_stage<BANDS, false, true>(stage, big);
+    return count ? pick_stage<BANDS, true, false>(stage, big) : pick_stage<BANDS, false, false>(stage, big);
+}
+
+}  // namespace
+
+cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFacts &dev, cudaStream_t stream,
+                         int *launches) {
+    const long long n_rays = a.ray_end - a.ray_begin;
+    if (n_rays <= 0 || a.p.max_bounce_count <= 0) return cudaSuccess;
+    if (a.bands != 1 && a.bands != 8) return cudaErrorInvalidValue;
+
+    // Staging mode by shared-memory footprint (16-byte barrier slot + planes).
+    const size_t geo_bytes = (size_t)a.n_walls * 16;
+    const size_t m1_bytes = ((size_t)a.n_walls * 8 + 15) & ~(size_t)15;
+    const size_t budget = (size_t)dev.smem_optin - 1024;
+    int stage;
+    size_t smem;
+    if (16 + 2 * geo_bytes + m1_bytes <= budget && 16 + 2 * geo_bytes + m1_bytes <= 96 * 1024) {
+        stage = 0;  // small scenes: everything on chip, several CTAs per SM still fit
+        smem = 16 + 2 * geo_bytes + m1_bytes;
+    } else if (16 + geo_bytes <= budget) {
+        stage = 1;
+        smem = 16 + geo_bytes;
+    } else {
+        stage = 2;
+        smem = 16;
+    }
+    // One CTA per SM once the planes take more than half of shared memory: use 1024 threads then.
+    const bool big_block = smem > (size_t)dev.smem_optin / 2;
+    const bool hits = a.hits != nullptr;
+    KernelChoice k = a.bands == 8 ? pick_mode<8>(count_tests, hits, stage, big_block)
+                                  : pick_mode<1>(count_tests, hits, stage, big_block);
+
+    cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+
+    // Block size: large enough to amortise the staging, small enough that small dispatches still
+    // cover the machine (config 1 traces only 15 040 rays).
+    int threads = k.max_threads;
+    if (!big_block) {
+        while (threads > 64 && (n_rays + threads - 1) / threads < 2LL * dev.sm_count) threads >>= 1;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long want = (n_rays + threads - 1) / threads;
+    long long cap = (long long)per_sm * dev.sm_count;
+    int grid = (int)(want < cap ? want : cap);
+
+    TraceLaunch arg = a;
+    void *params[] = {&arg};
+    e = cudaLaunchKernel(k.fn, dim3(grid), dim3(threads), params, smem, stream);
+    if (e == cudaSuccess && launches) ++*launches;
+    return e;
+}
+
+cudaError_t launch_fp32_peak(float *d_sink, int blocks, int threads, int iters, cudaStream_t stream) {
+    fp32_peak_kernel<<<blocks, threads, 0, stream>>>(d_sink, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace rar

@@ -74,3 +74,84 @@ int emu_trace(const rar_segment *walls, int n, const float *band_abs, const rar_
     }
     return 0;
 }
+
+// ---- FFT / partitioned overlap-save convolution: the same index logic as conv_kernels.cu ----------------
+#include <cmath>
+#include "../realisticaudioraytracing2d_b200/csrc/rar_fft.cuh"
+
+namespace {
+struct Tables {
+    rar::f2 tw[rar::kFftM], tw2[rar::kFftM / 2 + 1];
+    Tables() {
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int k = 0; k < rar::kFftM; k++) tw[k] = rar::f2{(float)std::cos(two_pi * k / rar::kFftM), (float)-std::sin(two_pi * k / rar::kFftM)};
+        for (int k = 0; k <= rar::kFftM / 2; k++)
+            tw2[k] = rar::f2{(float)std::cos(two_pi * k / (2 * rar::kFftM)), (float)-std::sin(two_pi * k / (2 * rar::kFftM))};
+    }
+};
+const Tables &tables() { static Tables t; return t; }
+
+void fft256(rar::f2 *a, rar::f2 *b, bool inverse) {
+    const Tables &t = tables();
+    const int ps[4] = {1, 4, 16, 64};
+    rar::f2 *src = a, *dst = b;
+    for (int s = 0; s < 4; s++) {
+        for (int i = 0; i < 64; i++) rar::fft_pass_r4(src, dst, i, ps[s], t.tw, inverse);
+        rar::f2 *tmp = src; src = dst; dst = tmp;
+    }  // four passes: result back in a
+}
+void rfft512(const float *w, rar::f2 *P) {
+    rar::f2 a[256], b[256];
+    for (int n = 0; n < 256; n++) a[n] = rar::f2{w[2 * n], w[2 * n + 1]};
+    fft256(a, b, false);
+    for (int k = 0; k <= 128; k++) rar::rfft_split(a, P, k, tables().tw2);
+}
+void irfft512(const rar::f2 *P, float *w) {  // w = 256 * true inverse
+    rar::f2 a[256], b[256];
+    for (int k = 0; k <= 128; k++) rar::irfft_merge(P, a, k, tables().tw2);
+    fft256(a, b, true);
+    for (int n = 0; n < 256; n++) { w[2 * n] = a[n].x; w[2 * n + 1] = a[n].y; }
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) void emu_rfft512(const float *w, float *P) { rfft512(w, (rar::f2 *)P); }
+extern "C" __attribute__((visibility("default"))) void emu_irfft512(const float *P, float *w) { irfft512((const rar::f2 *)P, w); }
+
+// The one-shot pipeline of rar_convolve_begin: input windows, per-block CMAC over partitions, output blocks.
+extern "C" __attribute__((visibility("default")))
+void emu_convolve(const float *x, int x_len, const float *ir, int ir_len, int accum, float *out) {
+    const int B = 256, out_len = x_len + ir_len;
+    for (int i = 0; i < out_len; i++) out[i] = 0.f;
+    if (accum <= 0 || x_len == 0 || ir_len == 0) return;
+    const int n_part = (ir_len + B - 1) / B, n_xwin = (x_len + B - 1) / B + 1, n_out = (out_len + B - 1) / B;
+    std::vector<rar::f2> H((size_t)n_part * B), X((size_t)n_xwin * B), Y(B);
+    float w[512];
+    for (int p = 0; p < n_part; p++) {
+        for (int t = 0; t < 512; t++) { long long g = (long long)p * B + t; w[t] = (t < B && g < ir_len) ? ir[g] : 0.f; }
+        rfft512(w, &H[(size_t)p * B]);
+    }
+    for (int j = 0; j < n_xwin; j++) {
+        for (int t = 0; t < 512; t++) {
+            long long g = ((long long)j - 1) * B + t;
+            float v = (g >= 0 && g < x_len) ? x[g] : 0.f;
+            w[t] = std::fabs(v) > 1e-4f ? v : 0.f;
+        }
+        rfft512(w, &X[(size_t)j * B]);
+    }
+    const float scale = (1.0f / (float)accum) / (float)B;
+    for (int j = 0; j < n_out; j++) {
+        int p_lo = j - (n_xwin - 1); if (p_lo < 0) p_lo = 0;
+        int p_hi = j < n_part - 1 ? j : n_part - 1;
+        for (int k = 0; k < B; k++) {
+            float re = 0, im = 0, ac = 0, bd = 0;
+            for (int p = p_lo; p <= p_hi; p++) {
+                rar::f2 a = X[(size_t)(j - p) * B + k], h = H[(size_t)p * B + k];
+                ac += a.x * h.x; bd += a.y * h.y; im += a.x * h.y + a.y * h.x;
+            }
+            re = ac - bd;
+            Y[k] = k == 0 ? rar::f2{ac, bd} : rar::f2{re, im};
+        }
+        irfft512(Y.data(), w);
+        for (int i = 0; i < B; i++) { long long o = (long long)j * B + i; if (o < out_len) out[o] = w[B + i] * scale; }
+    }
+}

@@ -1,0 +1,152 @@
+"""GPU parity of the partitioned overlap-save FFT convolution against the oracle's direct form
+(AudioConvolve.compute:13-31), through the C-ABI.  Bar: output within 1e-4 relative L2."""
+import numpy as np
+import pytest
+
+from realisticaudioraytracing2d_b200 import _capi, scenes
+from tests.common import capi_params, oracle_params, oracle_walls, rel_l2, trace_kwargs
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north star: convolved audio <= 1e-4 relative L2
+
+
+def _ir(n, seed=3):
+    return scenes.decaying_noise_ir(n, seed, decay_s=0.4)
+
+
+@pytest.mark.parametrize("n_in,n_ir", [(4800, 72000), (42624, 72000), (1000, 300), (256, 256), (257, 255), (5000, 1), (1, 1000), (3, 7)])
+def test_convolve_matches_direct_form(ctx, oracle, n_in, n_ir):
+    rng = np.random.default_rng(n_in * 31 + n_ir)
+    x = rng.uniform(-0.5, 0.5, n_in).astype(np.float32)
+    h = _ir(n_ir)
+    ctx.ir_write(0, h)
+    hq = ctx.ir_read(0, n_ir)                      # the IR as the slot holds it (Q23.40 quantised)
+    assert np.abs(hq - h).max() <= 2.0 ** -40
+    got = ctx.convolve(0, x, accum_count=3, ir_len=n_ir)
+    want = oracle.convolve(x, hq, 3)
+    assert got.shape == want.shape == (n_in + n_ir,)
+    assert rel_l2(got, want) <= TOL
+    assert got[-1] == 0.0                          # output has N+M samples, the last is always 0
+
+
+def test_epsilon_gate_and_accum_semantics(ctx, oracle):
+    rng = np.random.default_rng(5)
+    h = _ir(2000)
+    ctx.ir_write(0, h)
+    hq = ctx.ir_read(0, 2000)
+    x = rng.uniform(-0.5, 0.5, 3000).astype(np.float32)
+    x[::3] = rng.uniform(-1e-4, 1e-4, len(x[::3])).astype(np.float32)   # |x| <= eps contributes nothing (:25)
+    got = ctx.convolve(0, x, 2, 2000)
+    assert rel_l2(got, oracle.convolve(x, hq, 2)) <= TOL
+    xz = x.copy()
+    xz[np.abs(xz) <= np.float32(1e-4)] = 0
+    assert np.array_equal(got, ctx.convolve(0, xz, 2, 2000))
+    # accumCount <= 0 writes zeros (:30)
+    assert not ctx.convolve(0, x, 0, 2000).any()
+    # an impulse reproduces ir/accumCount, a delayed impulse shifts it
+    imp = np.zeros(700, np.float32)
+    imp[0] = 1.0
+    y = ctx.convolve(0, imp, 4, 2000)
+    assert rel_l2(y[:2000], hq / 4) <= TOL
+    imp = np.zeros(700, np.float32)
+    imp[333] = 1.0
+    y = ctx.convolve(0, imp, 1, 2000)
+    assert rel_l2(y[333:2333], hq) <= TOL and np.abs(y[:333]).max() <= 1e-6 * np.abs(hq).max()
+
+
+def test_async_tickets(ctx, oracle):
+    rng = np.random.default_rng(9)
+    h = _ir(5000)
+    ctx.ir_write(1, h)
+    hq = ctx.ir_read(1, 5000)
+    xs = [rng.uniform(-0.5, 0.5, 4800).astype(np.float32) for _ in range(3)]
+    tickets = [ctx.convolve_begin(1, x, 2) for x in xs]
+    assert len(set(tickets)) == 3
+    import time
+    t0 = time.time()
+    while not all(ctx.poll(t) for t in tickets):
+        assert time.time() - t0 < 30
+    for t, x in zip(tickets, xs):
+        assert rel_l2(ctx.convolve_end(t, 9800), oracle.convolve(x, hq, 2)) <= TOL
+    with pytest.raises(_capi.RarError):
+        ctx.poll(tickets[0])                       # retired
+
+
+def test_trace_then_convolve_config1(ctx, oracle):
+    """BASELINE config 1 end to end: bundled room, 3 accumulated frames, IR build + convolution of one clip."""
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    hist = np.zeros(n, np.int64)
+    for f in (11, 12, 13):
+        ctx.trace(capi_params(_capi, dict(kw, rng_state_offset=f)), 0)
+        oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, rng_state_offset=f)), hist=hist)
+    ir = ctx.ir_read(0, n)
+    assert np.array_equal(ir.view(np.uint32), oracle.ir_to_float(hist).view(np.uint32))
+    clip = scenes.synthetic_clip()
+    got = ctx.convolve(0, clip, 3, n)
+    want = oracle.convolve(clip, ir, 3)
+    assert rel_l2(got, want) <= TOL
+
+
+def test_streaming_convolver_matches_direct_form(ctx, oracle):
+    """Config 5 at reduced size: 6 streams with different IR lengths, 40 blocks of 256."""
+    rng = np.random.default_rng(21)
+    S, B, n_blocks, max_ir = 6, 256, 40, 5000
+    cv = _capi.Convolver(ctx, S, B, max_ir)
+    lens = [5000, 4097, 256, 1, 300, 2048]
+    irs = [_ir(L, seed=s) for s, L in enumerate(lens)]
+    for s, h in enumerate(irs):
+        cv.set_ir(s, h, scale=0.5)
+    x = rng.uniform(-1, 1, (S, n_blocks * B)).astype(np.float32)
+    x[:, ::11] *= 1e-5
+    y = np.concatenate([cv.process(x[:, k * B:(k + 1) * B]) for k in range(n_blocks)], axis=1)
+    for s in range(S):
+        want = oracle.convolve(x[s], irs[s] * np.float32(0.5), 1)[: n_blocks * B]
+        assert rel_l2(y[s], want) <= TOL, s
+    # reset restarts the streams
+    cv.reset()
+    y2 = cv.process(x[:, :B])
+    assert np.array_equal(y2, y[:, :B])
+    cv.destroy()
+
+
+def test_streaming_convolver_from_traced_slot(ctx, oracle):
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc, impulse_length=24000)
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, 24000, 1)
+    ctx.trace(capi_params(_capi, kw), 0)
+    ir = ctx.ir_read(0, 24000)
+    cv = _capi.Convolver(ctx, 2, 256, 24000)
+    cv.set_ir_from_slot(0, 0, 1)
+    cv.set_ir_from_slot(1, 0, 2)
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, (2, 100 * 256)).astype(np.float32)
+    y = np.concatenate([cv.process(x[:, k * 256:(k + 1) * 256]) for k in range(100)], axis=1)
+    assert rel_l2(y[0], oracle.convolve(x[0], ir, 1)[: 100 * 256]) <= TOL
+    assert rel_l2(y[1], oracle.convolve(x[1], ir, 2)[: 100 * 256]) <= TOL
+    cv.destroy()
+
+
+def test_streaming_full_size_properties(ctx):
+    """Config 5 shape at full partition count on a few streams (10 s IR = 1875 partitions):
+    impulse in -> IR out (block by block), and linearity."""
+    S, B, n_ir = 4, 256, 480000
+    cv = _capi.Convolver(ctx, S, B, n_ir)
+    irs = [_ir(n_ir, seed=40 + s) for s in range(S)]
+    for s in range(S):
+        cv.set_ir(s, irs[s])
+    x0 = np.zeros((S, B), np.float32)
+    x0[:, 5] = 1.0
+    outs = [cv.process(x0)]
+    z = np.zeros((S, B), np.float32)
+    for _ in range(30):
+        outs.append(cv.process(z))
+    y = np.concatenate(outs, axis=1)
+    for s in range(S):
+        assert rel_l2(y[s, 5:], irs[s][: y.shape[1] - 5]) <= TOL
+    cv.destroy()

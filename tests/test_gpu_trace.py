@@ -1,0 +1,198 @@
+"""GPU parity of the trace kernel against the CPU oracle, through the C-ABI.
+
+Bars (BASELINE.json north_star): integer histogram bins bit-exact; hit distance <= 1e-5 relative.
+Because the kernel and the oracle obey the same binary32 arithmetic contract the hit lists are in
+fact expected to be bit-identical; the test asserts that and reports the relative error otherwise.
+"""
+import numpy as np
+import pytest
+
+from realisticaudioraytracing2d_b200 import _capi, scenes
+from tests.common import capi_params, oracle_params, oracle_walls, sort_hits, trace_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(ctx, O, sc, kw, frames=(1,)):
+    bands = kw["bands"]
+    n_words = kw["impulse_length"] * bands
+    ctx.set_walls(sc.walls)
+    if bands > 1:
+        ctx.set_wall_band_absorption(sc.band_absorption)
+    ctx.ir_clear(0, kw["impulse_length"], bands)
+    ctx.get_counters(reset=True)
+    hist = np.zeros(n_words, dtype=np.int64)
+    ctr = None
+    for f in frames:
+        k = dict(kw, rng_state_offset=f)
+        ctx.trace(capi_params(_capi, dict(k, flags=k["flags"] | _capi.RAR_FLAG_COUNT_TESTS)), 0)
+        r = O.trace(oracle_walls(O, sc.walls), oracle_params(O, k), band_abs=sc.band_absorption if bands > 1 else None, hist=hist)
+        ctr = r.counters if ctr is None else {a: ctr[a] + r.counters[a] for a in ctr}
+    got = ctx.ir_read_fixed(0, n_words)
+    return got, hist, ctx.get_counters(), ctr
+
+
+@pytest.mark.parametrize("name,frames", [("smoll", (1, 2, 3)), ("big", (1,)), ("smoll1000", (7,))])
+def test_bundled_rooms_histogram_bit_exact(ctx, oracle, name, frames):
+    sc = scenes.big_room() if name == "big" else scenes.smoll_room()
+    kw = trace_kwargs(sc, ray_count=1000 if name == "smoll1000" else sc.ray_count)
+    got, want, gc, oc = _run_pair(ctx, oracle, sc, kw, frames)
+    assert np.count_nonzero(want) > 500
+    assert np.array_equal(got, want)
+    assert gc == oc
+
+
+def test_shoebox_histogram_bit_exact(ctx, oracle):
+    sc = scenes.shoebox(ray_count=200_000, max_bounces=32)
+    got, want, gc, oc = _run_pair(ctx, oracle, sc, trace_kwargs(sc))
+    assert np.array_equal(got, want)
+    assert gc == oc
+
+
+def test_shoebox_scattering_transmission_bit_exact(ctx, oracle):
+    sc = scenes.shoebox(ray_count=100_000, max_bounces=16, scattering=0.35, transmission=0.2, ior=1.3)
+    got, want, gc, oc = _run_pair(ctx, oracle, sc, trace_kwargs(sc))
+    assert np.array_equal(got, want)
+    assert gc == oc
+
+
+@pytest.mark.parametrize("bands", [1, 8])
+def test_maze_histogram_bit_exact(ctx, oracle, bands):
+    sc = scenes.maze(n_segments=2000, ray_count=20_000, max_bounces=24, bands=8)
+    got, want, gc, oc = _run_pair(ctx, oracle, sc, trace_kwargs(sc, bands=bands))
+    assert np.count_nonzero(want) > 100
+    assert np.array_equal(got, want)
+    assert gc == oc
+
+
+@pytest.mark.parametrize("n_segments", [5000, 10000, 16000])
+def test_large_scene_staging_modes_bit_exact(ctx, oracle, n_segments):
+    # 5000 walls: endpoint plane in shared memory, materials global; 10000: 160 KB plane, one CTA per SM;
+    # 16000: does not fit in shared memory, read-only global path.
+    sc = scenes.maze(n_segments=n_segments, ray_count=4096, max_bounces=8, bands=8)
+    got, want, gc, oc = _run_pair(ctx, oracle, sc, trace_kwargs(sc, bands=1))
+    assert np.array_equal(got, want)
+    assert gc == oc
+
+
+def test_hit_list_matches_oracle(ctx, oracle):
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc)
+    ctx.set_walls(sc.walls)
+    hits, keys, n = ctx.trace_hits(capi_params(_capi, kw), capacity=sc.ray_count * sc.max_bounces * 2 + 1024)
+    r = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw), want_hist=False, want_hits=True)
+    assert n == r.n_hits == len(hits)
+    hits, keys = sort_hits(hits, keys)
+    assert np.array_equal(keys["ray"], r.hits["ray"]) and np.array_equal(keys["bounce"], r.hits["bounce"])
+    assert np.array_equal(keys["kind"], r.hits["kind"])
+    # tolerance of the north star: arrival time (distance / c) within 1e-5 relative
+    rel = np.abs(hits["time_delay"].astype(np.float64) - r.hits["time_delay"]) / r.hits["time_delay"]
+    assert rel.max() <= 1e-5
+    # and, stronger, bit identity of every field
+    assert np.array_equal(hits["time_delay"].view(np.uint32), r.hits["time_delay"].view(np.uint32))
+    assert np.array_equal(hits["energy"].view(np.uint32), r.hits["energy"].view(np.uint32))
+    assert np.array_equal(hits["hit_point"][:, 0].view(np.uint32), r.hits["hit_x"].view(np.uint32))
+    assert np.array_equal(hits["hit_point"][:, 1].view(np.uint32), r.hits["hit_y"].view(np.uint32))
+
+
+def test_ray_range_sharding_is_bit_identical(ctx, oracle):
+    """Rays sharded by contiguous id range (the multi-GPU partition) sum to the unsharded histogram."""
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace(capi_params(_capi, kw), 0)
+    whole = ctx.ir_read_fixed(0, n)
+    ctx.ir_clear(1, n, 1)
+    total = 15040
+    for lo, hi in [(0, 3000), (3000, 3001), (3001, 9999), (9999, total)]:
+        ctx.trace(capi_params(_capi, dict(kw, ray_begin=lo, ray_end=hi)), 1)
+    assert np.array_equal(ctx.ir_read_fixed(1, n), whole)
+
+
+def test_exact_ray_count_flag_and_dispatch_rounding(ctx, oracle):
+    sc = scenes.smoll_room()
+    for flags in (0, _capi.RAR_FLAG_EXACT_RAY_COUNT):
+        kw = trace_kwargs(sc, ray_count=1001, flags=flags)
+        got, want, gc, oc = _run_pair(ctx, oracle, sc, kw)
+        assert np.array_equal(got, want)
+        assert gc == oc
+
+
+def test_edge_cases(ctx, oracle):
+    sc = scenes.smoll_room()
+    n = 4800
+    # no walls at all: only direct listener crossings, rays end after one iteration
+    empty = sc.walls[:0]
+    ctx.set_walls(empty)
+    ctx.ir_clear(0, n, 1)
+    kw = trace_kwargs(sc, ray_count=4096, impulse_length=n, source=(0.0, 0.0), listener=(3.0, 0.0))
+    ctx.trace(capi_params(_capi, kw), 0)
+    r = oracle.trace(empty.view(oracle.SEGMENT_DTYPE), oracle_params(oracle, kw))
+    assert np.array_equal(ctx.ir_read_fixed(0, n), r.hist) and np.count_nonzero(r.hist) > 0
+    # zero bounces: nothing is deposited
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace(capi_params(_capi, trace_kwargs(sc, max_bounce_count=0, impulse_length=n)), 0)
+    assert not ctx.ir_read_fixed(0, n).any()
+    # impulse response shorter than the arrivals: late hits are dropped, not wrapped
+    kw = trace_kwargs(sc, impulse_length=3000)
+    got, want, _, _ = _run_pair(ctx, oracle, sc, kw)
+    assert np.array_equal(got, want)
+    # a single ray
+    kw = trace_kwargs(sc, ray_count=1, flags=_capi.RAR_FLAG_EXACT_RAY_COUNT)
+    got, want, _, _ = _run_pair(ctx, oracle, sc, kw)
+    assert np.array_equal(got, want)
+
+
+def test_error_behaviour(ctx):
+    sc = scenes.smoll_room()
+    ctx.set_walls(sc.walls)
+    with pytest.raises(_capi.RarError):
+        ctx.trace(capi_params(_capi, trace_kwargs(sc)), 9)          # slot never configured
+    ctx.ir_clear(0, 100, 1)
+    with pytest.raises(_capi.RarError):
+        ctx.trace(capi_params(_capi, trace_kwargs(sc)), 0)          # impulse_length mismatch
+    with pytest.raises(_capi.RarError):
+        ctx.trace(capi_params(_capi, trace_kwargs(sc, bands=3, impulse_length=100)), 0)
+    assert not ctx.ir_read_fixed(5, 16).any()                        # unconfigured slot reads as zeros
+
+
+def test_debug_rays(ctx):
+    sc = scenes.smoll_room()
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, sc.impulse_length, 1)
+    ctx.trace(capi_params(_capi, trace_kwargs(sc, debug_ray_count=100)), 0)
+    rays = ctx.get_debug_rays(100 * (sc.max_bounces + 1)).reshape(100, sc.max_bounces + 1, 4)
+    assert np.allclose(rays[:, 0, 0], sc.source[0]) and np.allclose(rays[:, 0, 1], sc.source[1])
+    assert np.all(rays[:, 0, 2] == np.float32(sc.input_gain))
+    assert np.all(rays[:, 1, 2] == np.float32(sc.input_gain))       # energy before the first absorption
+
+
+def test_full_size_shoebox_properties(ctx, oracle):
+    """BASELINE config 2 at full size (1M rays x 32 bounces): size-independent checks.
+    (a) linearity in input_gain by a power of two is exact in fixed point up to the truncation of each deposit;
+    (b) the histogram is independent of how the ray range is split;
+    (c) the first arrival is the direct path at (|S-L| - r)/c."""
+    sc = scenes.shoebox()
+    kw = trace_kwargs(sc)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace(capi_params(_capi, kw), 0)
+    whole = ctx.ir_read_fixed(0, n)
+    ctx.ir_clear(1, n, 1)
+    cuts = [0, 1 << 18, 3 << 18, (1 << 20) - 7, 1 << 20]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        ctx.trace(capi_params(_capi, dict(kw, ray_begin=lo, ray_end=hi)), 1)
+    assert np.array_equal(ctx.ir_read_fixed(1, n), whole)
+    first = int(np.flatnonzero(whole)[0])
+    d = np.hypot(sc.listener[0] - sc.source[0], sc.listener[1] - sc.source[1]) - sc.listener_radius
+    assert abs(first - d / sc.speed_of_sound * sc.sample_rate) <= 1.5
+    # oracle on a 1/64 sample of the same dispatch
+    sub = dict(kw, ray_begin=123_456, ray_end=123_456 + 16_384)
+    ctx.ir_clear(1, n, 1)
+    ctx.trace(capi_params(_capi, sub), 1)
+    r = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, sub))
+    assert np.array_equal(ctx.ir_read_fixed(1, n), r.hist)
