@@ -23,6 +23,8 @@
  *     cross(a,b) := fmaf(a.x, b.y, -(a.y*b.x))
  *     p + d*t    := fmaf(d, t, p)
  *     length(v)  := sqrtf(dot(v,v));  normalize(v) := v * (1.0f / length(v))
+ *     v / s      := v * (1.0f / s) for a 2-vector v and a scalar s (the reading of HLSL's
+ *                   vector/scalar division that GPU compilers emit: one reciprocal, two multiplies)
  *     reflect(i,n) := i - (2*dot(i,n))*n  evaluated as fmaf(-(2*dot), n, i)
  *     lerp(a,b,s)  := fmaf(s, b-a, a)
  *   - sin/cos/asin are the fixed polynomial kernels orc_sincosf/orc_asinf below
@@ -241,7 +243,8 @@ static void emit(const trace_env *env, uint32_t ray, int bounce, int kind, float
 
 /* Raytrace2D.compute:40-47 */
 static int check_vis(const trace_env *env, float sx, float sy, float ex, float ey, float dist, orc_counters *ctr) {
-    float dx = (ex - sx) / dist, dy = (ey - sy) / dist;
+    float inv_dist = 1.0f / dist; /* (end - start) / dist as vector * (1/scalar) */
+    float dx = (ex - sx) * inv_dist, dy = (ey - sy) * inv_dist;
     float lim = dist - 0.1f;
     for (int w = 0; w < env->n_walls; w++) {
         const orc_segment *s = &env->walls[w];
@@ -311,7 +314,8 @@ static void trace_one(const trace_env *env, uint32_t id, orc_counters *ctr) {
             if (check_vis(env, sx, sy, p->listener_x, p->listener_y, dl, ctr)) {
                 int flip = dot2(dirx, diry, wall->nx, wall->ny) > 0.0f;
                 float enx = flip ? -wall->nx : wall->nx, eny = flip ? -wall->ny : wall->ny;
-                float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx / dl, tly / dl));
+                float inv_dl = 1.0f / dl; /* toList / distList as vector * (1/scalar) */
+                float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
                 float total = dist + dl;
                 float geo = (cos_t * 0.5f);
                 float inv = 1.0f / (total * total);

@@ -78,50 +78,88 @@ RAR_HD void ray_init(RayState<BANDS> &r, uint32_t id, const RayConsts &p) {
     }
 }
 
-// Literal Common.hlsl:14-21 on the precomputed edge e = b - a; used on filter survivors only.
+// Common.hlsl:14-21 on the precomputed edge e = b - a; used on filter survivors only.  t1 is the
+// correctly rounded quotient the literal formula returns.  The test on t2 = fl(num2/dotP) needs no
+// division: for binary32 values fl(num2/dotP) <= 1 <=> |num2| <= |dotP| (a > b > 0 implies a/b > 1 + 2^-24,
+// which cannot round down to 1), and fl(num2/dotP) >= 0 <=> num2 is zero or has the sign of dotP (the only
+// other way is a quotient of opposite signs underflowing to -0, |num2/dotP| <= 2^-150, which the filter
+// has already excluded -- see the header comment).
 RAR_HD float intersect_exact(float num1, float num2, float dotP) {
     if (fabsf(dotP) < kEps) return kInf;
-    float t1 = rar_div(num1, dotP);
-    float t2 = rar_div(num2, dotP);
-    return (t1 >= kEps && t2 >= 0.0f && t2 <= 1.0f) ? t1 : kInf;
+    const float t1 = rar_div(num1, dotP);
+    const bool same_sign = (num2 >= 0.0f) == (dotP >= 0.0f);
+    const bool t2_ok = (num2 == 0.0f || same_sign) && fabsf(num2) <= fabsf(dotP);
+    return (t1 >= kEps && t2_ok) ? t1 : kInf;
 }
 
 constexpr float kSlack = 1.00000095367431640625f;  // 1 + 2^-20
 
-// Raytrace2D.compute:69-72: nearest hit over all walls, lowest index wins ties.
+// The per-wall quantities of the filter (see the header comment).
+struct WallTest {
+    float dotP, num1, num2;
+};
+RAR_HD WallTest wall_test(const f4 s, float ox, float oy, float dx, float ndy) {
+    WallTest t;
+    const float v1x = ox - s.x, v1y = oy - s.y;
+    t.dotP = rar_fma(s.z, ndy, s.w * dx);
+    t.num2 = rar_fma(v1x, ndy, v1y * dx);
+    t.num1 = rar_fma(s.z, v1y, -(s.w * v1x));
+    return t;
+}
+// bound_m = (closest or shadow limit) * (1 + 2^-20).  A stale (larger) bound only loosens the filter.
+RAR_HD bool wall_pass(const WallTest &t, float bound_m) {
+    const float r = bound_m * t.dotP;
+    return (fabsf(rar_fma(2.0f, t.num2, -t.dotP)) <= fabsf(t.dotP)) & (fabsf(rar_fma(2.0f, t.num1, -r)) <= fabsf(r));
+}
+
+// Raytrace2D.compute:69-72: nearest hit over all walls, lowest index wins ties.  Walls are filtered four
+// at a time against the same bound so that the common case is four independent loads, four filters and
+// a single branch; survivors are then evaluated literally, in wall order.
 template <class Scene>
 RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy, float &closest_out, int &hit_out) {
     float closest = kInf, closest_m = kInf * kSlack;
     int hit = -1;
     const float ndy = -dy;
     const int n = sc.n_walls();
-#pragma unroll 4
-    for (int w = 0; w < n; w++) {
-        const f4 s = sc.geo(w);
-        float v1x = ox - s.x, v1y = oy - s.y;
-        float dotP = rar_fma(s.z, ndy, s.w * dx);
-        float num2 = rar_fma(v1x, ndy, v1y * dx);
-        float num1 = rar_fma(s.z, v1y, -(s.w * v1x));
-        float r = closest_m * dotP;
-        bool pass = (fabsf(rar_fma(2.0f, num2, -dotP)) <= fabsf(dotP)) & (fabsf(rar_fma(2.0f, num1, -r)) <= fabsf(r));
-        if (pass) {
-            float d = intersect_exact(num1, num2, dotP);
-            if (d < closest) {
-                closest = d;
-                closest_m = d * kSlack;
-                hit = w;
-            }
+    int w = 0;
+#define RAR_NEAREST_EXACT(T, W)                                      \
+    {                                                                \
+        const float d = intersect_exact((T).num1, (T).num2, (T).dotP); \
+        if (d < closest) {                                           \
+            closest = d;                                             \
+            closest_m = d * kSlack;                                  \
+            hit = (W);                                               \
+        }                                                            \
+    }
+    for (; w + 4 <= n; w += 4) {
+        const WallTest t0 = wall_test(sc.geo(w), ox, oy, dx, ndy);
+        const WallTest t1 = wall_test(sc.geo(w + 1), ox, oy, dx, ndy);
+        const WallTest t2 = wall_test(sc.geo(w + 2), ox, oy, dx, ndy);
+        const WallTest t3 = wall_test(sc.geo(w + 3), ox, oy, dx, ndy);
+        const bool p0 = wall_pass(t0, closest_m), p1 = wall_pass(t1, closest_m);
+        const bool p2 = wall_pass(t2, closest_m), p3 = wall_pass(t3, closest_m);
+        if (p0 | p1 | p2 | p3) {
+            if (p0) RAR_NEAREST_EXACT(t0, w)
+            if (p1) RAR_NEAREST_EXACT(t1, w + 1)
+            if (p2) RAR_NEAREST_EXACT(t2, w + 2)
+            if (p3) RAR_NEAREST_EXACT(t3, w + 3)
         }
     }
+    for (; w < n; w++) {
+        const WallTest t = wall_test(sc.geo(w), ox, oy, dx, ndy);
+        if (wall_pass(t, closest_m)) RAR_NEAREST_EXACT(t, w)
+    }
+#undef RAR_NEAREST_EXACT
     closest_out = closest;
     hit_out = hit;
 }
 
 // Raytrace2D.compute:40-47 checkVis.  Returns true when visible; *tests receives the number of
-// intersect() evaluations the reference's early-exit loop performs.
+// intersect() evaluations the reference's early-exit loop performs (index of the first blocking wall + 1).
 template <class Scene>
 RAR_HD bool check_vis(const Scene &sc, float sx, float sy, float ex, float ey, float dist, int *tests) {
-    float dx = rar_div(ex - sx, dist), dy = rar_div(ey - sy, dist);
+    const float inv_dist = rar_rcp(dist);  // vector / scalar := vector * (1 / scalar)
+    float dx = (ex - sx) * inv_dist, dy = (ey - sy) * inv_dist;
     const float lim = dist - 0.1f;
     const int n = sc.n_walls();
     if (n > 0 && kInf < lim) {  // every intersect() result (<= inf) is < lim: blocked by wall 0
@@ -131,23 +169,29 @@ RAR_HD bool check_vis(const Scene &sc, float sx, float sy, float ex, float ey, f
     const float lim_m = lim * kSlack;
     const float ndy = -dy;
     int w = 0;
-    bool blocked = false;
-#pragma unroll 4
-    for (; w < n; w++) {
-        const f4 s = sc.geo(w);
-        float v1x = sx - s.x, v1y = sy - s.y;
-        float dotP = rar_fma(s.z, ndy, s.w * dx);
-        float num2 = rar_fma(v1x, ndy, v1y * dx);
-        float num1 = rar_fma(s.z, v1y, -(s.w * v1x));
-        float r = lim_m * dotP;
-        bool pass = (fabsf(rar_fma(2.0f, num2, -dotP)) <= fabsf(dotP)) & (fabsf(rar_fma(2.0f, num1, -r)) <= fabsf(r));
-        if (pass) {
-            float d = intersect_exact(num1, num2, dotP);
-            if (d < lim) { blocked = true; break; }
+    int first = -1;  // first blocking wall
+    for (; w + 4 <= n; w += 4) {
+        const WallTest t0 = wall_test(sc.geo(w), sx, sy, dx, ndy);
+        const WallTest t1 = wall_test(sc.geo(w + 1), sx, sy, dx, ndy);
+        const WallTest t2 = wall_test(sc.geo(w + 2), sx, sy, dx, ndy);
+        const WallTest t3 = wall_test(sc.geo(w + 3), sx, sy, dx, ndy);
+        const bool p0 = wall_pass(t0, lim_m), p1 = wall_pass(t1, lim_m);
+        const bool p2 = wall_pass(t2, lim_m), p3 = wall_pass(t3, lim_m);
+        if (p0 | p1 | p2 | p3) {
+            if (p0 && intersect_exact(t0.num1, t0.num2, t0.dotP) < lim) { first = w; break; }
+            if (p1 && intersect_exact(t1.num1, t1.num2, t1.dotP) < lim) { first = w + 1; break; }
+            if (p2 && intersect_exact(t2.num1, t2.num2, t2.dotP) < lim) { first = w + 2; break; }
+            if (p3 && intersect_exact(t3.num1, t3.num2, t3.dotP) < lim) { first = w + 3; break; }
         }
     }
-    if (tests) *tests = blocked ? w + 1 : n;
-    return !blocked;
+    if (first < 0) {
+        for (; w < n; w++) {
+            const WallTest t = wall_test(sc.geo(w), sx, sy, dx, ndy);
+            if (wall_pass(t, lim_m) && intersect_exact(t.num1, t.num2, t.dotP) < lim) { first = w; break; }
+        }
+    }
+    if (tests) *tests = first >= 0 ? first + 1 : n;
+    return first < 0;
 }
 
 // One iteration of the bounce loop, Raytrace2D.compute:66-155.  Returns false when the ray ended.
@@ -216,10 +260,11 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
         if (vis) {
             bool flip = dir_dot_n > 0.0f;
             float enx = flip ? -wnx : wnx, eny = flip ? -wny : wny;
-            float cos_t = fmaxf(0.0f, dot2(enx, eny, rar_div(tlx, dl), rar_div(tly, dl)));
+            const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
+            float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
             float total = r.dist + dl;
             float geo = cos_t * 0.5f;
-            float inv = rar_div(1.0f, total * total);
+            float inv = rar_rcp(total * total);
             float contrib = ((r.energy * keep) * geo) * inv;
             if (contrib > 1e-5f) {
                 nee.has = 1;
@@ -245,12 +290,14 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
 
     const bool entering = dir_dot_n < 0.0f;  // :124-128
     const float nx = entering ? wnx : -wnx, ny = entering ? wny : -wny;
-    const float wall_speed = rar_div(p.speed_of_sound, m1.y);
-    const float next_speed = entering ? wall_speed : ((r.wall_depth <= 1) ? p.speed_of_sound : wall_speed);
-    const float eta = rar_div(next_speed, r.speed);
-    const float rng_val = pcg_random(r.rng);  // :129
+    const float rng_val = pcg_random(r.rng);  // :129 (always drawn)
 
     if (rng_val < m1.x) {  // :131-147
+        // wallSpeed / nextSpeed / eta (:126-128) are only consumed here; evaluating them lazily gives the
+        // same values.
+        const float wall_speed = rar_div(p.speed_of_sound, m1.y);
+        const float next_speed = entering ? wall_speed : ((r.wall_depth <= 1) ? p.speed_of_sound : wall_speed);
+        const float eta = rar_div(next_speed, r.speed);
         float rx, ry;
         refract2(r.dx, r.dy, nx, ny, eta, rx, ry);
         if (rar_sqrt(dot2(rx, ry, rx, ry)) > 0.0f) {
@@ -263,7 +310,7 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
                 rx = jx;
                 ry = jy;
             }
-            float inv = rar_div(1.0f, rar_sqrt(dot2(rx, ry, rx, ry)));
+            float inv = rar_rcp(rar_sqrt(dot2(rx, ry, rx, ry)));
             r.dx = rx * inv;
             r.dy = ry * inv;
             r.speed = next_speed;
@@ -278,15 +325,24 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
     // :149-154.  dir_dot_n with the flipped normal is exactly +-dir_dot_n (negation is exact).
     const float k2 = 2.0f * (entering ? dir_dot_n : -dir_dot_n);
     const float spx = rar_fma(-k2, nx, r.dx), spy = rar_fma(-k2, ny, r.dy);
-    const float u = rar_fma(2.0f, pcg_random(r.rng), -1.0f);
-    const float ang = asin_poly(u);
-    float s, c;
-    sincos_poly(ang, s, c);
-    const float dfx = rar_fma(nx, c, -(ny * s));
-    const float dfy = rar_fma(nx, s, ny * c);
-    const float mx = rar_fma(m0.w, dfx - spx, spx);
-    const float my = rar_fma(m0.w, dfy - spy, spy);
-    const float inv = rar_div(1.0f, rar_sqrt(dot2(mx, my, mx, my)));
+    const float u = rar_fma(2.0f, pcg_random(r.rng), -1.0f);  // always drawn (:150)
+    float mx, my;
+    if (m0.w == 0.0f && spx != 0.0f && spy != 0.0f) {
+        // lerp(spec, diff, 0) = fma(0, diff - spec, spec) = spec exactly when spec != 0 (0 * finite = +-0 and
+        // x + +-0 = x); only a zero component could pick up the sign of diff - spec, so that case takes
+        // the general path below.
+        mx = spx;
+        my = spy;
+    } else {
+        const float ang = asin_poly(u);
+        float s, c;
+        sincos_poly(ang, s, c);
+        const float dfx = rar_fma(nx, c, -(ny * s));
+        const float dfy = rar_fma(nx, s, ny * c);
+        mx = rar_fma(m0.w, dfx - spx, spx);
+        my = rar_fma(m0.w, dfy - spy, spy);
+    }
+    const float inv = rar_rcp(rar_sqrt(dot2(mx, my, mx, my)));
     r.dx = mx * inv;
     r.dy = my * inv;
     r.px = rar_fma(nx, kEps, r.px);

@@ -79,3 +79,13 @@ def convolve(x, ir, accum):
     out = np.zeros(len(x) + len(ir), np.float32)
     lib().emu_convolve(C.c_void_p(x.ctypes.data), len(x), C.c_void_p(ir.ctypes.data), len(ir), int(accum), C.c_void_p(out.ctypes.data))
     return out
+
+
+def intersect_many(rays, segs, closest):
+    rays = np.ascontiguousarray(rays, np.float32)
+    segs = np.ascontiguousarray(segs, np.float32)
+    closest = np.ascontiguousarray(closest, np.float32)
+    out = np.zeros(len(rays), np.float32)
+    lib().emu_intersect_many(C.c_void_p(rays.ctypes.data), C.c_void_p(segs.ctypes.data), C.c_void_p(closest.ctypes.data),
+                             len(rays), C.c_void_p(out.ctypes.data))
+    return out

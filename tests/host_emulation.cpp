@@ -155,3 +155,19 @@ void emu_convolve(const float *x, int x_len, const float *ir, int ir_len, int ac
         for (int i = 0; i < B; i++) { long long o = (long long)j * B + i; if (o < out_len) out[o] = w[B + i] * scale; }
     }
 }
+
+// Single ray-segment test through the product's filter + exact path (bound = closest), for comparison
+// with the oracle's literal Common.hlsl:14-21.
+extern "C" __attribute__((visibility("default")))
+void emu_intersect_many(const float *rays /*ox,oy,dx,dy*/, const float *segs /*ax,ay,bx,by*/, const float *closest,
+                        int n, float *out) {
+    for (int i = 0; i < n; i++) {
+        const float *r = rays + 4 * i, *s = segs + 4 * i;
+        volatile float ex = s[2] - s[0], ey = s[3] - s[1];
+        rar::f4 g{s[0], s[1], ex, ey};
+        rar::WallTest t = rar::wall_test(g, r[0], r[1], r[2], -r[3]);
+        float d = rar::kInf;
+        if (rar::wall_pass(t, closest[i] * rar::kSlack)) d = rar::intersect_exact(t.num1, t.num2, t.dotP);
+        out[i] = d < closest[i] ? d : rar::kInf;
+    }
+}

@@ -1,0 +1,122 @@
+"""CPU checks of the product's device headers compiled for the host (tests/host_emulation.cpp) against
+the independent oracle: the conservative intersection filter, the batched inner loops, the lazy /
+specular shortcuts and the fixed-point deposit must reproduce the oracle bit for bit; the hand-written
+FFT and the partitioned overlap-save pipeline must stay within the 1e-4 relative-L2 bar.
+
+These run without a GPU and are NOT a product path: they exist so that logic errors are caught here
+before GPU time is spent.  The GPU parity tests proper are tests/test_gpu_*.py.
+"""
+import numpy as np
+import pytest
+
+from realisticaudioraytracing2d_b200 import scenes
+from tests import emulation
+from tests.common import oracle_params, oracle_walls, rel_l2, trace_kwargs
+
+
+def _check(O, sc, kw):
+    P = oracle_params(O, kw)
+    ba = sc.band_absorption if kw["bands"] > 1 else None
+    r = O.trace(oracle_walls(O, sc.walls), P, band_abs=ba, want_hits=True)
+    hist, hits, ctr = emulation.trace(O, sc.walls, P, ba)
+    assert np.array_equal(hist, r.hist)
+    assert len(hits) == len(r.hits) and hits.tobytes() == r.hits.tobytes()
+    assert ctr == r.counters
+    return r
+
+
+@pytest.mark.parametrize("frame", [1, 2, 77])
+def test_smoll_room(oracle, frame):
+    sc = scenes.smoll_room()
+    r = _check(oracle, sc, trace_kwargs(sc, rng_state_offset=frame))
+    assert r.counters["ray_bounces"] > 75000
+
+
+def test_big_room_ten_bounces(oracle):
+    sc = scenes.big_room()
+    _check(oracle, sc, trace_kwargs(sc, max_bounce_count=10))
+
+
+@pytest.mark.parametrize("scattering,transmission,ior", [(0.0, 0.0, 1.0), (0.3, 0.0, 1.0), (0.0, 0.4, 1.4), (0.7, 0.5, 0.6)])
+def test_shoebox_materials(oracle, scattering, transmission, ior):
+    sc = scenes.shoebox(ray_count=20000, max_bounces=32, scattering=scattering, transmission=transmission, ior=ior)
+    _check(oracle, sc, trace_kwargs(sc))
+
+
+def test_shoebox_axis_aligned_rays_hit_zero_components(oracle):
+    # 4 rays: directions are (almost) axis aligned; specular directions get exact-zero components, the case
+    # the specular shortcut must hand to the general path.
+    sc = scenes.shoebox(ray_count=4, max_bounces=16)
+    sc.source = (5.0, 3.0)
+    for frame in range(1, 40):
+        _check(oracle, sc, trace_kwargs(sc, ray_count=4, rng_state_offset=frame, flags=1))
+
+
+@pytest.mark.parametrize("bands", [1, 8])
+@pytest.mark.parametrize("n_segments", [1000, 1003])
+def test_maze(oracle, bands, n_segments):
+    sc = scenes.maze(n_segments=n_segments, ray_count=3000, max_bounces=16, bands=8)
+    _check(oracle, sc, trace_kwargs(sc, bands=bands))
+
+
+@pytest.mark.parametrize("n_walls", [0, 1, 2, 3, 5, 7])
+def test_wall_counts_around_the_batch_size(oracle, n_walls):
+    sc = scenes.smoll_room()
+    sc.walls = sc.walls[[0, 4, 8, 12, 16, 17, 18][:n_walls]] if n_walls else sc.walls[:0]
+    _check(oracle, sc, trace_kwargs(sc, ray_count=2000))
+
+
+def test_fft_against_numpy():
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        w = rng.standard_normal(512).astype(np.float32)
+        got = emulation.rfft512(w).astype(np.complex128)
+        ref = np.fft.rfft(w.astype(np.float64))
+        assert abs(got[0].real - ref[0].real) <= 1e-4 and abs(got[0].imag - ref[256].real) <= 1e-4   # packed DC / Nyquist
+        assert np.abs(got[1:] - ref[1:256]).max() <= 2e-6 * np.abs(ref).max() * 10
+        assert np.abs(emulation.irfft512(got.astype(np.complex64)) - w).max() <= 2e-6
+
+
+@pytest.mark.parametrize("n_in,n_ir", [(4800, 72000), (1000, 300), (256, 256), (257, 255), (5000, 1), (3, 7)])
+def test_partitioned_convolution_against_direct_form(oracle, n_in, n_ir):
+    rng = np.random.default_rng(n_in + n_ir)
+    x = rng.uniform(-0.5, 0.5, n_in).astype(np.float32)
+    x[::7] *= np.float32(1e-4)
+    h = scenes.decaying_noise_ir(n_ir, 3, decay_s=0.4)
+    got = emulation.convolve(x, h, 3)
+    want = oracle.convolve(x, h, 3)
+    assert rel_l2(got, want) <= 1e-4
+
+
+def test_filtered_intersection_equals_literal_formula(oracle):
+    """The division-free filter + exact path against the oracle's literal `intersect`, on random and
+    adversarial inputs: axis-aligned rays and walls, rays through wall endpoints, near-parallel pairs,
+    tiny and huge scales."""
+    rng = np.random.default_rng(11)
+    n = 200_000
+    o = rng.uniform(-50, 50, (n, 2))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    d = np.stack([np.cos(ang), np.sin(ang)], 1)
+    a = rng.uniform(-50, 50, (n, 2))
+    b = a + rng.uniform(-30, 30, (n, 2))
+    k = n // 8
+    d[:k] = np.array([[1, 0], [0, 1], [-1, 0], [0, -1]])[rng.integers(0, 4, k)]        # axis-aligned rays
+    b[k:2 * k, 0] = a[k:2 * k, 0]                                                      # vertical walls
+    b[2 * k:3 * k, 1] = a[2 * k:3 * k, 1]                                              # horizontal walls
+    t = rng.uniform(0.5, 40, k)[:, None]
+    a[3 * k:4 * k] = o[3 * k:4 * k] + d[3 * k:4 * k] * t                               # ray through endpoint a
+    b[4 * k:5 * k] = o[4 * k:5 * k] + d[4 * k:5 * k] * t                               # ray through endpoint b
+    b[5 * k:6 * k] = a[5 * k:6 * k] + d[5 * k:6 * k] * t + rng.normal(0, 1e-5, (k, 2))  # nearly parallel
+    scale = np.ones(n)
+    scale[6 * k:7 * k] = 1e-3
+    scale[7 * k:] = 1e4
+    o, a, b = o * scale[:, None], a * scale[:, None], b * scale[:, None]
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    segs = np.concatenate([a, b], 1).astype(np.float32)
+    closest = np.where(rng.random(n) < 0.5, 1e8, rng.uniform(0.1, 60, n) * scale).astype(np.float32)
+    got = emulation.intersect_many(rays, segs, closest)
+    L = oracle.lib()
+    want = np.array([L.orc_intersect(*map(float, rays[i]), *map(float, segs[i])) for i in range(n)], np.float32)
+    want = np.where(want < closest, want, np.float32(1e8))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (want < 1e8).sum() > n // 20
