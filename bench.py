@@ -135,16 +135,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-class _Cai:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from realisticaudioraytracing2d_b200 import _capi, scenes
+    from realisticaudioraytracing2d_b200.host import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,11 +167,10 @@ def run_ours(args):
     # ---- workload ------------------------------------------------------------------------------
     sc = scenes.shoebox(ray_count=RAYS_PER_GPU * world, max_bounces=BOUNCES)
     n_bins = sc.impulse_length
-    lo, hi = rank * RAYS_PER_GPU, (rank + 1) * RAYS_PER_GPU
+    lo, hi = sharding.shard_range(RAYS_PER_GPU * world, rank, world)
     ctx.set_walls(sc.walls)
     ctx.ir_clear(0, n_bins, 1)
-    ptr, n_words = ctx.ir_device_ptr(0)
-    hist_t = torch.as_tensor(_Cai(ptr, n_words), device=dev)
+    hist_t = sharding.DeviceHistogram(ctx, 0, dev).tensor
 
     def params(frame, flags=0):
         return _capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
@@ -184,8 +179,7 @@ def run_ours(args):
     def step(frame):
         ctx.ir_clear(0, n_bins, 1)
         ctx.trace(params(frame), 0)
-        if world > 1:
-            dist.all_reduce(hist_t, op=dist.ReduceOp.SUM)
+        sharding.allreduce_histogram(hist_t)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -236,8 +230,7 @@ def run_ours(args):
         ctx.set_walls(walls_host)                      # H2D: 40 B per wall
         ctx.ir_clear(0, n_bins, 1)
         ctx.trace(params(frame), 0)
-        if world > 1:
-            dist.all_reduce(hist_t, op=dist.ReduceOp.SUM)
+        sharding.allreduce_histogram(hist_t)
         ir_host[:] = ctx.ir_read(0, n_bins)            # D2H: the float IR
 
     for w in range(min(args.warmup, 3)):

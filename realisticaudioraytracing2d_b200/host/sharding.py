@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing of the ray stage: contiguous ray-id ranges per rank and one integer all-reduce.
+
+One process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in the CPU tests).  Rays
+are independent -- the RNG is a pure function of the global ray id and the frame
+(Raytrace2D.compute:51) -- so rank r of W traces the thread ids [r*N/W, (r+1)*N/W) of one dispatch into
+its private Q23.40 histogram, and a single all-reduce(sum, int64) of bins x bands words produces the
+complete histogram on every rank.  Integer addition commutes, so the result is bit-identical for any W.
+Batched listeners / streams shard by contiguous batch range with no collective at all.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of `total` items for `rank` of `world`; sizes differ by at most one."""
+    if world <= 0 or not (0 <= rank < world) or total < 0:
+        raise ValueError("bad shard arguments")
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def dispatched_threads(ray_count: int, exact: bool = False) -> int:
+    """Threads the reference's Trace dispatch runs: ceil(rayCount/64)*64 unless `exact`
+    (Raytrace2D.compute:49-52, Helpers/ComputeHelper.cs:27-31)."""
+    return ray_count if exact else (ray_count + 63) // 64 * 64
+
+
+def allreduce_histogram(hist_tensor, group=None) -> None:
+    """In-place sum of the int64 histogram over all ranks (a no-op outside a process group)."""
+    import torch
+    import torch.distributed as dist
+    if hist_tensor.dtype != torch.int64:
+        raise TypeError("the impulse-response histogram is int64 fixed point")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist_tensor, op=dist.ReduceOp.SUM, group=group)
+
+
+class DeviceHistogram:
+    """Zero-copy torch view of a context's IR slot (rar_ir_device_ptr) for the collective."""
+
+    def __init__(self, ctx, slot: int, device):
+        import torch
+        ptr, n = ctx.ir_device_ptr(slot)
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        self.tensor = torch.as_tensor(self, device=device)

@@ -1,0 +1,46 @@
+"""world_size-2 check (gloo, CPU) of the multi-GPU plumbing: each rank holds the histogram of its own
+contiguous ray-id range, one all-reduce(sum, int64) gives every rank the complete histogram, and the result
+equals the unsharded trace bit for bit.  The per-rank histograms come from the oracle here (no GPU in this
+container); on the GPU box the same helpers drive the CUDA path (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from realisticaudioraytracing2d_b200 import scenes
+from realisticaudioraytracing2d_b200.host.sharding import allreduce_histogram, dispatched_threads, shard_range
+from tests.common import oracle_params, oracle_walls, trace_kwargs
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc, ray_count=3000)
+    lo, hi = shard_range(dispatched_threads(3000), rank, world)
+    part = O.trace(oracle_walls(O, sc.walls), oracle_params(O, dict(kw, ray_begin=lo, ray_end=hi)), n_threads=2).hist
+    t = torch.from_numpy(part.copy())
+    allreduce_histogram(t)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_is_bit_identical_to_one_rank(tmp_path, oracle):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sc = scenes.smoll_room()
+    whole = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, trace_kwargs(sc, ray_count=3000))).hist
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"rank{r}.npy"), whole)
+
+
+def test_allreduce_is_a_noop_without_a_process_group():
+    t = torch.arange(8, dtype=torch.int64)
+    allreduce_histogram(t)
+    assert t.tolist() == list(range(8))
