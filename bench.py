@@ -90,8 +90,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _host_threads() -> int:
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1; ignore that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def _oracle_step_sample(O, scenes, n_gpus: int, rays: int, frame: int, threads: int = 0):
     """One bounded sample of the workload on the CPU oracle; returns (tests, seconds)."""
+    threads = threads or _host_threads()
     sc = scenes.shoebox(ray_count=RAYS_PER_GPU * n_gpus, max_bounces=BOUNCES)
     P = O.make_params(source_x=sc.source[0], source_y=sc.source[1], listener_x=sc.listener[0], listener_y=sc.listener[1],
                       listener_radius=sc.listener_radius, speed_of_sound=sc.speed_of_sound, input_gain=sc.input_gain,
@@ -112,7 +121,7 @@ def run_reference(args):
     from oracle import oracle as O
     from realisticaudioraytracing2d_b200 import scenes
     O.build()
-    cores = O.num_threads()
+    cores = _host_threads()
     rays = RAYS_PER_GPU  # bounded sample: one GPU's share of the dispatch per step (a fraction of a second)
     for w in range(args.warmup):
         _oracle_step_sample(O, scenes, args.gpus, rays, 1000 + w)
@@ -281,7 +290,7 @@ def run_ours(args):
             n_acc += t
             t_acc += dt
             k += 1
-        cpu = {"value": n_acc / t_acc, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+        cpu = {"value": n_acc / t_acc, "unit": UNIT, "cores": _host_threads(), "kind": "port",
                "sample": f"{k} x rays [0,{rays}) of the same dispatch x {BOUNCES} bounces ({t_acc:.1f} s of CPU work)"}
 
     if rank == 0:
