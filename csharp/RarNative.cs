@@ -62,6 +62,7 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_ir_device_ptr(IntPtr ctx, int slot, out IntPtr devicePtr, out long nWords);
 
         [DllImport(Lib)] public static extern int rar_trace(IntPtr ctx, ref RarTraceParams p, int slot);
+        [DllImport(Lib)] public static extern int rar_trace_listeners(IntPtr ctx, ref RarTraceParams p, [In] float[] listenersXY, int nListeners, int firstSlot);
         [DllImport(Lib)] public static extern int rar_trace_hits(IntPtr ctx, ref RarTraceParams p, IntPtr hits, IntPtr keys, long capacity, out long count);
         [DllImport(Lib)] public static extern int rar_get_counters(IntPtr ctx, out RarCounters c, int reset);
         [DllImport(Lib)] public static extern int rar_get_debug_rays(IntPtr ctx, [Out] UnityEngine.Vector4[] dst, long nFloat4);

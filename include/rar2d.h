@@ -180,6 +180,13 @@ RAR_API int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr,
  * params->bands must match the slot's configuration. */
 RAR_API int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot);
 
+/* BASELINE config 4 (batched auralisation): the same dispatch traced for n_listeners listener positions
+ * (listeners_xy = x0,y0,x1,y1,...; params->listener_pos is ignored); listener l accumulates into slot
+ * first_slot + l, each of which must be configured like `slot` of rar_trace.  Equivalent to n_listeners
+ * calls of rar_trace.  Asynchronous.  Listeners shard across GPUs by contiguous range with no exchange. */
+RAR_API int rar_trace_listeners(rar_context *ctx, const rar_trace_params *params, const float *listeners_xy,
+                                int32_t n_listeners, int32_t first_slot);
+
 /* Same trace, but the arrivals are returned instead of binned: the contents of the reference's
  * rayInfoBuffer (AppendStructuredBuffer<RayInfo>, Raytrace2D.compute:82,116), unordered, with the
  * producing ray/bounce in `keys` (may be NULL).  *count receives the number produced (may exceed

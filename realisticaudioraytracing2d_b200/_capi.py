@@ -64,6 +64,7 @@ SYMBOLS = {
     "rar_ir_write": (C.c_int, [_p, _i32, _p, _i32, _i32]),
     "rar_ir_device_ptr": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64)]),
     "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
+    "rar_trace_listeners": (C.c_int, [_p, C.POINTER(TraceParams), _p, _i32, _i32]),
     "rar_trace_hits": (C.c_int, [_p, C.POINTER(TraceParams), _p, _p, _i64, C.POINTER(_i64)]),
     "rar_get_counters": (C.c_int, [_p, C.POINTER(Counters), _i32]),
     "rar_get_debug_rays": (C.c_int, [_p, _p, _i64]),
@@ -210,6 +211,10 @@ class Context:
     # trace ------------------------------------------------------------------------------------
     def trace(self, params: TraceParams, slot: int) -> None:
         self._ck(self._lib.rar_trace(self._h, C.byref(params), slot))
+
+    def trace_listeners(self, params: TraceParams, listeners_xy: np.ndarray, first_slot: int) -> None:
+        xy = np.ascontiguousarray(listeners_xy, dtype=np.float32).reshape(-1, 2)
+        self._ck(self._lib.rar_trace_listeners(self._h, C.byref(params), xy.ctypes.data if len(xy) else None, len(xy), first_slot))
 
     def trace_hits(self, params: TraceParams, capacity: int):
         hits = np.zeros(capacity, dtype=RAY_INFO_DTYPE)

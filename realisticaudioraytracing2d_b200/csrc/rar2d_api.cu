@@ -473,6 +473,22 @@ int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) {
     return RAR_OK;
 }
 
+int rar_trace_listeners(rar_context *ctx, const rar_trace_params *params, const float *listeners_xy, int32_t n_listeners,
+                        int32_t first_slot) {
+    RAR_ENTER(ctx);
+    if (!params) return fail(ctx, RAR_ERR_INVALID, "null params");
+    if (n_listeners < 0 || (n_listeners > 0 && !listeners_xy)) return fail(ctx, RAR_ERR_INVALID, "bad listener array");
+    if (first_slot < 0 || (long long)first_slot + n_listeners > kMaxSlots) return fail(ctx, RAR_ERR_INVALID, "slot range out of bounds");
+    for (int l = 0; l < n_listeners; l++) {
+        rar_trace_params p = *params;
+        p.listener_pos[0] = listeners_xy[2 * l];
+        p.listener_pos[1] = listeners_xy[2 * l + 1];
+        int rc = rar_trace(ctx, &p, first_slot + l);
+        if (rc != RAR_OK) return rc;
+    }
+    return RAR_OK;
+}
+
 int rar_trace_hits(rar_context *ctx, const rar_trace_params *params, rar_ray_info *hits, rar_hit_key *keys,
                    int64_t capacity, int64_t *count) {
     RAR_ENTER(ctx);

@@ -196,3 +196,19 @@ def test_full_size_shoebox_properties(ctx, oracle):
     ctx.trace(capi_params(_capi, sub), 1)
     r = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, sub))
     assert np.array_equal(ctx.ir_read_fixed(1, n), r.hist)
+
+
+def test_batched_listeners_config4_shape(ctx, oracle):
+    """BASELINE config 4 at reduced size: one source, a grid of listeners, one IR slot per listener; every slot
+    must equal the oracle's histogram for that listener."""
+    sc = scenes.maze(n_segments=400, ray_count=4096, max_bounces=5, bands=8)
+    kw = trace_kwargs(sc, bands=1, impulse_length=24000)
+    gx, gy = np.meshgrid(np.linspace(20, 60, 3), np.linspace(25, 55, 2))
+    listeners = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.float32)
+    ctx.set_walls(sc.walls)
+    for l in range(len(listeners)):
+        ctx.ir_clear(10 + l, 24000, 1)
+    ctx.trace_listeners(capi_params(_capi, kw), listeners, 10)
+    for l, (lx, ly) in enumerate(listeners):
+        want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, listener=(float(lx), float(ly))))).hist
+        assert np.array_equal(ctx.ir_read_fixed(10 + l, 24000), want), l
