@@ -154,57 +154,102 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
     hit_out = hit;
 }
 
-// Raytrace2D.compute:40-47 checkVis.  Returns true when visible; *tests receives the number of
-// intersect() evaluations the reference's early-exit loop performs (index of the first blocking wall + 1).
-template <class Scene>
-RAR_HD bool check_vis(const Scene &sc, float sx, float sy, float ex, float ey, float dist, int *tests) {
+// ---- shadow ray (Raytrace2D.compute:40-47 checkVis) -------------------------------------------------
+
+// The shadow ray of one next-event estimate, ready to be tested against the walls.
+struct ShadowRay {
+    float sx, sy;   // start = hit point + stored normal * eps (:105)
+    float dx, ndy;  // direction (end - start) * (1/dist): not unit length, as in the reference; ndy = -dy
+    float lim;      // dist - 0.1: a wall hit closer than this blocks (:44)
+};
+
+RAR_HD ShadowRay make_shadow_ray(float sx, float sy, float ex, float ey, float dist) {
+    ShadowRay q;
     const float inv_dist = rar_rcp(dist);  // vector / scalar := vector * (1 / scalar)
-    float dx = (ex - sx) * inv_dist, dy = (ey - sy) * inv_dist;
-    const float lim = dist - 0.1f;
+    q.sx = sx;
+    q.sy = sy;
+    q.dx = (ex - sx) * inv_dist;
+    q.ndy = -((ey - sy) * inv_dist);
+    q.lim = dist - 0.1f;
+    return q;
+}
+
+// Does wall record s block the shadow ray?  (filter, then the literal formula for survivors)
+RAR_HD bool shadow_blocked_by(const f4 s, const ShadowRay &q, float lim_m) {
+    const WallTest t = wall_test(s, q.sx, q.sy, q.dx, q.ndy);
+    return wall_pass(t, lim_m) && intersect_exact(t.num1, t.num2, t.dotP) < q.lim;
+}
+
+// One thread walks all walls with the reference's early exit.  Returns true when visible; *tests receives
+// the number of intersect() evaluations the reference's loop performs (first blocking wall + 1, else n).
+template <class Scene>
+RAR_HD bool check_vis(const Scene &sc, const ShadowRay &q, int *tests) {
     const int n = sc.n_walls();
-    if (n > 0 && kInf < lim) {  // every intersect() result (<= inf) is < lim: blocked by wall 0
+    if (n > 0 && kInf < q.lim) {  // every intersect() result (<= inf) is < lim: blocked by wall 0
         if (tests) *tests = 1;
         return false;
     }
-    const float lim_m = lim * kSlack;
-    const float ndy = -dy;
+    const float lim_m = q.lim * kSlack;
     int w = 0;
     int first = -1;  // first blocking wall
     for (; w + 4 <= n; w += 4) {
-        const WallTest t0 = wall_test(sc.geo(w), sx, sy, dx, ndy);
-        const WallTest t1 = wall_test(sc.geo(w + 1), sx, sy, dx, ndy);
-        const WallTest t2 = wall_test(sc.geo(w + 2), sx, sy, dx, ndy);
-        const WallTest t3 = wall_test(sc.geo(w + 3), sx, sy, dx, ndy);
+        const WallTest t0 = wall_test(sc.geo(w), q.sx, q.sy, q.dx, q.ndy);
+        const WallTest t1 = wall_test(sc.geo(w + 1), q.sx, q.sy, q.dx, q.ndy);
+        const WallTest t2 = wall_test(sc.geo(w + 2), q.sx, q.sy, q.dx, q.ndy);
+        const WallTest t3 = wall_test(sc.geo(w + 3), q.sx, q.sy, q.dx, q.ndy);
         const bool p0 = wall_pass(t0, lim_m), p1 = wall_pass(t1, lim_m);
         const bool p2 = wall_pass(t2, lim_m), p3 = wall_pass(t3, lim_m);
         if (p0 | p1 | p2 | p3) {
-            if (p0 && intersect_exact(t0.num1, t0.num2, t0.dotP) < lim) { first = w; break; }
-            if (p1 && intersect_exact(t1.num1, t1.num2, t1.dotP) < lim) { first = w + 1; break; }
-            if (p2 && intersect_exact(t2.num1, t2.num2, t2.dotP) < lim) { first = w + 2; break; }
-            if (p3 && intersect_exact(t3.num1, t3.num2, t3.dotP) < lim) { first = w + 3; break; }
+            if (p0 && intersect_exact(t0.num1, t0.num2, t0.dotP) < q.lim) { first = w; break; }
+            if (p1 && intersect_exact(t1.num1, t1.num2, t1.dotP) < q.lim) { first = w + 1; break; }
+            if (p2 && intersect_exact(t2.num1, t2.num2, t2.dotP) < q.lim) { first = w + 2; break; }
+            if (p3 && intersect_exact(t3.num1, t3.num2, t3.dotP) < q.lim) { first = w + 3; break; }
         }
     }
     if (first < 0) {
         for (; w < n; w++) {
-            const WallTest t = wall_test(sc.geo(w), sx, sy, dx, ndy);
-            if (wall_pass(t, lim_m) && intersect_exact(t.num1, t.num2, t.dotP) < lim) { first = w; break; }
+            if (shadow_blocked_by(sc.geo(w), q, lim_m)) { first = w; break; }
         }
     }
     if (tests) *tests = first >= 0 ? first + 1 : n;
     return first < 0;
 }
 
-// One iteration of the bounce loop, Raytrace2D.compute:66-155.  Returns false when the ray ended.
-// dbg_hit / dbg_miss: where to record this bounce's vertex for the debugRays buffer (:87-88, :96-97), or
-// nullptr.
+// ---- one iteration of the bounce loop (Raytrace2D.compute:66-155) in three phases --------------------
+//
+//   bounce_begin : nearest hit, direct listener crossing, advance, and everything of the next-event
+//                  estimate that does not need the shadow ray (:69-104, :106-112 reordered);
+//   shadow phase : visibility of the listener from the hit point (:105) -- check_vis() per thread, or the
+//                  warp-cooperative version in trace_kernel.cu;
+//   bounce_finish: emit the estimate if visible (:113-118), absorb (:121-122), transmit or reflect (:124-154).
+//
+// The reference evaluates checkVis before it knows whether the estimate clears the 1e-5 threshold (:111).
+// checkVis has no side effect, so the phases compute the contribution first and resolve the shadow ray
+// only when the result can matter (WITH COUNT the shadow ray is always resolved, so that the test counters
+// are the reference's).
+
+template <int BANDS>
+struct BounceCtx {
+    int hit;            // wall index, -1: ray left the scene
+    int want_shadow;    // the shadow ray must be resolved
+    int nee_candidate;  // contribution clears the threshold (deposit iff visible)
+    ShadowRay shadow;
+    f4 m0;              // nx, ny, absorption, scattering
+    f2 m1;              // transmission, ior
+    float keep, dir_dot_n;
+    float nee_t, nee_e, geo, inv;
+    float band_keep[BANDS > 1 ? BANDS : 1];
+};
+
+// Returns false when the ray ended without hitting a wall (:86-90).
 template <int BANDS, bool COUNT, class Scene>
-RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
-                       Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg_hit = nullptr, f4 *dbg_miss = nullptr) {
+RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
+                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg_hit = nullptr, f4 *dbg_miss = nullptr) {
     direct.has = 0;
-    nee.has = 0;
+    c.want_shadow = 0;
+    c.nee_candidate = 0;
     float closest;
-    int hit;
-    nearest_hit(sc, r.px, r.py, r.dx, r.dy, closest, hit);  // :69-72
+    nearest_hit(sc, r.px, r.py, r.dx, r.dy, closest, c.hit);  // :69-72
     if (COUNT) {
         ctr->ray_bounces += 1;
         ctr->nearest_tests += (unsigned long long)sc.n_walls();
@@ -227,7 +272,7 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
             if (COUNT) ctr->direct_hits += 1;
         }
     }
-    if (hit < 0) {  // :86-90
+    if (c.hit < 0) {  // :86-90
         if (dbg_miss) *dbg_miss = f4{rar_fma(r.dx, 20.0f, r.px), rar_fma(r.dy, 20.0f, r.py), 0.0f, 0.0f};
         return false;
     }
@@ -238,75 +283,85 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
     r.dist += closest;
     if (dbg_hit) *dbg_hit = f4{r.px, r.py, r.energy, 0.0f};  // :96-97
 
-    const f4 m0 = sc.mat0(hit);  // nx, ny, absorption, scattering   (:99)
-    const f2 m1 = sc.mat1(hit);  // transmission, ior
-    const float wnx = m0.x, wny = m0.y;
-    const float keep = 1.0f - m0.z;
-    float band_keep[BANDS > 1 ? BANDS : 1];
+    c.m0 = sc.mat0(c.hit);  // :99
+    c.m1 = sc.mat1(c.hit);
+    const float wnx = c.m0.x, wny = c.m0.y;
+    c.keep = 1.0f - c.m0.z;
     if (BANDS > 1) {
-        const float *ba = sc.band_abs(hit);
+        const float *ba = sc.band_abs(c.hit);
 #pragma unroll
-        for (int b = 0; b < BANDS; b++) band_keep[b] = 1.0f - ba[b];
+        for (int b = 0; b < BANDS; b++) c.band_keep[b] = 1.0f - ba[b];
     }
-    const float dir_dot_n = dot2(r.dx, r.dy, wnx, wny);
+    c.dir_dot_n = dot2(r.dx, r.dy, wnx, wny);
 
-    if (r.wall_depth == 0) {  // :101-119
-        float tlx = p.listener_x - r.px, tly = p.listener_y - r.py;
-        float dl = rar_sqrt(dot2(tlx, tly, tlx, tly));
-        float sx = rar_fma(wnx, kEps, r.px), sy = rar_fma(wny, kEps, r.py);
-        int tests = 0;
-        bool vis = check_vis(sc, sx, sy, p.listener_x, p.listener_y, dl, COUNT ? &tests : nullptr);
-        if (COUNT) ctr->shadow_tests += (unsigned long long)tests;
-        if (vis) {
-            bool flip = dir_dot_n > 0.0f;
-            float enx = flip ? -wnx : wnx, eny = flip ? -wny : wny;
-            const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
-            float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
-            float total = r.dist + dl;
-            float geo = cos_t * 0.5f;
-            float inv = rar_rcp(total * total);
-            float contrib = ((r.energy * keep) * geo) * inv;
-            if (contrib > 1e-5f) {
-                nee.has = 1;
-                nee.hx = r.px;
-                nee.hy = r.py;
-                nee.t = r.time + rar_div(dl, p.speed_of_sound);
-                nee.e = contrib;
-                if (BANDS > 1) {
-#pragma unroll
-                    for (int b = 0; b < BANDS; b++) nee.band_e[b] = ((r.band_e[b] * band_keep[b]) * geo) * inv;
-                }
-                if (COUNT) ctr->nee_hits += 1;
-            }
+    if (r.wall_depth == 0) {  // :101-112
+        const float tlx = p.listener_x - r.px, tly = p.listener_y - r.py;
+        const float dl = rar_sqrt(dot2(tlx, tly, tlx, tly));
+        const bool flip = c.dir_dot_n > 0.0f;
+        const float enx = flip ? -wnx : wnx, eny = flip ? -wny : wny;
+        const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
+        const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
+        const float total = r.dist + dl;
+        c.geo = cos_t * 0.5f;
+        c.inv = rar_rcp(total * total);
+        c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
+        c.nee_candidate = c.nee_e > 1e-5f;
+        c.want_shadow = COUNT ? 1 : c.nee_candidate;
+        if (c.want_shadow) {
+            c.shadow = make_shadow_ray(rar_fma(wnx, kEps, r.px), rar_fma(wny, kEps, r.py), p.listener_x, p.listener_y, dl);
+            c.nee_t = r.time + rar_div(dl, p.speed_of_sound);
         }
     }
+    return true;
+}
 
-    r.energy *= keep;  // :121-122
+// `visible` is the outcome of the shadow phase (ignored unless c.want_shadow).  Returns false when the ray
+// ended (energy below 1e-3, :122).
+template <int BANDS, bool COUNT, class Scene>
+RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &nee,
+                          const BounceCtx<BANDS> &c, bool visible, RayCounters *ctr) {
+    (void)sc;
+    nee.has = 0;
+    if (c.nee_candidate && visible) {  // :113-118
+        nee.has = 1;
+        nee.hx = r.px;
+        nee.hy = r.py;
+        nee.t = c.nee_t;
+        nee.e = c.nee_e;
+        if (BANDS > 1) {
+#pragma unroll
+            for (int b = 0; b < BANDS; b++) nee.band_e[b] = ((r.band_e[b] * c.band_keep[b]) * c.geo) * c.inv;
+        }
+        if (COUNT) ctr->nee_hits += 1;
+    }
+
+    r.energy *= c.keep;  // :121-122
     if (BANDS > 1) {
 #pragma unroll
-        for (int b = 0; b < BANDS; b++) r.band_e[b] *= band_keep[b];
+        for (int b = 0; b < BANDS; b++) r.band_e[b] *= c.band_keep[b];
     }
     if (r.energy < 1e-3f) return false;
 
-    const bool entering = dir_dot_n < 0.0f;  // :124-128
+    const float wnx = c.m0.x, wny = c.m0.y;
+    const bool entering = c.dir_dot_n < 0.0f;  // :124-128
     const float nx = entering ? wnx : -wnx, ny = entering ? wny : -wny;
     const float rng_val = pcg_random(r.rng);  // :129 (always drawn)
 
-    if (rng_val < m1.x) {  // :131-147
+    if (rng_val < c.m1.x) {  // :131-147
         // wallSpeed / nextSpeed / eta (:126-128) are only consumed here; evaluating them lazily gives the
         // same values.
-        const float wall_speed = rar_div(p.speed_of_sound, m1.y);
+        const float wall_speed = rar_div(p.speed_of_sound, c.m1.y);
         const float next_speed = entering ? wall_speed : ((r.wall_depth <= 1) ? p.speed_of_sound : wall_speed);
         const float eta = rar_div(next_speed, r.speed);
         float rx, ry;
         refract2(r.dx, r.dy, nx, ny, eta, rx, ry);
         if (rar_sqrt(dot2(rx, ry, rx, ry)) > 0.0f) {
-            if (m0.w > 0.0f) {
-                float jitter = (pcg_random(r.rng) - 0.5f) * 2.0f * m0.w;
-                float s, c;
-                sincos_poly(jitter, s, c);
-                float jx = rar_fma(rx, c, -(ry * s));
-                float jy = rar_fma(rx, s, ry * c);
+            if (c.m0.w > 0.0f) {
+                float jitter = (pcg_random(r.rng) - 0.5f) * 2.0f * c.m0.w;
+                float sn, cs;
+                sincos_poly(jitter, sn, cs);
+                float jx = rar_fma(rx, cs, -(ry * sn));
+                float jy = rar_fma(rx, sn, ry * cs);
                 rx = jx;
                 ry = jy;
             }
@@ -322,12 +377,12 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
         }
     }
 
-    // :149-154.  dir_dot_n with the flipped normal is exactly +-dir_dot_n (negation is exact).
-    const float k2 = 2.0f * (entering ? dir_dot_n : -dir_dot_n);
+    // :149-154.  dot(dir, n) with the flipped normal is exactly +-dot(dir, wall.normal) (negation is exact).
+    const float k2 = 2.0f * (entering ? c.dir_dot_n : -c.dir_dot_n);
     const float spx = rar_fma(-k2, nx, r.dx), spy = rar_fma(-k2, ny, r.dy);
     const float u = rar_fma(2.0f, pcg_random(r.rng), -1.0f);  // always drawn (:150)
     float mx, my;
-    if (m0.w == 0.0f && spx != 0.0f && spy != 0.0f) {
+    if (c.m0.w == 0.0f && spx != 0.0f && spy != 0.0f) {
         // lerp(spec, diff, 0) = fma(0, diff - spec, spec) = spec exactly when spec != 0 (0 * finite = +-0 and
         // x + +-0 = x); only a zero component could pick up the sign of diff - spec, so that case takes
         // the general path below.
@@ -335,12 +390,12 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
         my = spy;
     } else {
         const float ang = asin_poly(u);
-        float s, c;
-        sincos_poly(ang, s, c);
-        const float dfx = rar_fma(nx, c, -(ny * s));
-        const float dfy = rar_fma(nx, s, ny * c);
-        mx = rar_fma(m0.w, dfx - spx, spx);
-        my = rar_fma(m0.w, dfy - spy, spy);
+        float sn, cs;
+        sincos_poly(ang, sn, cs);
+        const float dfx = rar_fma(nx, cs, -(ny * sn));
+        const float dfy = rar_fma(nx, sn, ny * cs);
+        mx = rar_fma(c.m0.w, dfx - spx, spx);
+        my = rar_fma(c.m0.w, dfy - spy, spy);
     }
     const float inv = rar_rcp(rar_sqrt(dot2(mx, my, mx, my)));
     r.dx = mx * inv;
@@ -348,6 +403,22 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
     r.px = rar_fma(nx, kEps, r.px);
     r.py = rar_fma(ny, kEps, r.py);
     return true;
+}
+
+// The three phases with a per-thread shadow walk: what a single thread of the reference does.
+template <int BANDS, bool COUNT, class Scene>
+RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
+                       Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg_hit = nullptr, f4 *dbg_miss = nullptr) {
+    BounceCtx<BANDS> c;
+    nee.has = 0;
+    if (!bounce_begin<BANDS, COUNT>(sc, p, r, direct, c, ctr, dbg_hit, dbg_miss)) return false;
+    bool visible = true;
+    if (c.want_shadow) {
+        int tests = 0;
+        visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
+        if (COUNT) ctr->shadow_tests += (unsigned long long)tests;
+    }
+    return bounce_finish<BANDS, COUNT>(sc, p, r, nee, c, visible, ctr);
 }
 
 }  // namespace rar

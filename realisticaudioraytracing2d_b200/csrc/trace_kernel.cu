@@ -148,9 +148,55 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+// ---- warp-cooperative shadow rays -------------------------------------------------------------------
+//
+// In a large scene a per-thread checkVis walk wastes the warp: a lane whose shadow ray is blocked early
+// idles while its neighbours scan all n walls.  Here the warp takes the pending shadow rays one at a time;
+// the 32 lanes test 64 consecutive walls per iteration (conflict-free 16-byte shared-memory reads) and a
+// ballot finds the first blocking wall, which is exactly where the reference's loop would have stopped.
+// Work per shadow ray is proportional to the tests the reference performs, not to n.
+template <bool COUNT, class Scene>
+__device__ __forceinline__ bool coop_shadow(const Scene &sc, bool pending, const ShadowRay &q, unsigned lane,
+                                            RayCounters &ctr) {
+    unsigned need = __ballot_sync(kFull, pending);
+    bool my_vis = true;
+    const int n = sc.n_walls();
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        ShadowRay b;
+        b.sx = __shfl_sync(kFull, q.sx, src);
+        b.sy = __shfl_sync(kFull, q.sy, src);
+        b.dx = __shfl_sync(kFull, q.dx, src);
+        b.ndy = __shfl_sync(kFull, q.ndy, src);
+        b.lim = __shfl_sync(kFull, q.lim, src);
+        int first = -1;
+        if (n > 0 && kInf < b.lim) {
+            first = 0;  // every intersect() result (<= inf) is < lim: wall 0 blocks
+        } else {
+            const float lim_m = b.lim * kSlack;
+            for (int base = 0; base < n; base += 64) {
+                const int w0 = base + (int)lane, w1 = w0 + 32;
+                const bool k0 = w0 < n && shadow_blocked_by(sc.geo(w0), b, lim_m);
+                const bool k1 = w1 < n && shadow_blocked_by(sc.geo(w1), b, lim_m);
+                const unsigned m0 = __ballot_sync(kFull, k0), m1 = __ballot_sync(kFull, k1);
+                if (m0 | m1) {
+                    first = m0 ? base + __ffs(m0) - 1 : base + 32 + __ffs(m1) - 1;
+                    break;
+                }
+            }
+        }
+        if (lane == (unsigned)src) {
+            my_vis = first < 0;
+            if (COUNT) ctr.shadow_tests += (unsigned long long)(first >= 0 ? first + 1 : n);
+        }
+    }
+    return my_vis;
+}
+
 // ---- the kernel -------------------------------------------------------------------------------------
 
-template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT>
+template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP>
 __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -214,12 +260,27 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
         for (int i = 0; i < max_b; i++) {
             if (!__any_sync(kFull, alive)) break;
             Arrival<BANDS> direct, nee;
+            BounceCtx<BANDS> c;
             direct.has = 0;
             nee.has = 0;
+            c.want_shadow = 0;
+            c.shadow = ShadowRay{0.f, 0.f, 0.f, 0.f, 0.f};
+            bool hit_wall = false;
             if (alive) {
-                alive = ray_bounce<BANDS, COUNT>(sc, a.p, r, direct, nee, &ctr, dbg100 ? dbg + i + 1 : nullptr,
-                                                 dbgN ? dbg + i + 1 : nullptr);
+                hit_wall = bounce_begin<BANDS, COUNT>(sc, a.p, r, direct, c, &ctr, dbg100 ? dbg + i + 1 : nullptr,
+                                                      dbgN ? dbg + i + 1 : nullptr);
             }
+            const bool pending = hit_wall && c.want_shadow;
+            bool visible = true;
+            if (COOP) {
+                __syncwarp();
+                visible = coop_shadow<COUNT>(sc, pending, c.shadow, lane, ctr);
+            } else if (pending) {
+                int tests = 0;
+                visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
+                if (COUNT) ctr.shadow_tests += (unsigned long long)tests;
+            }
+            if (alive) alive = hit_wall && bounce_finish<BANDS, COUNT>(sc, a.p, r, nee, c, visible, &ctr);
             __syncwarp();
             if (HITS) {
                 emit_hit(a, direct, id, i, 0);
@@ -264,23 +325,25 @@ struct KernelChoice {
     int max_threads;
 };
 
-template <int BANDS, bool COUNT, bool HITS, int STAGE>
-KernelChoice pick_maxt(bool big_block) {
-    if (big_block) return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, STAGE, 1024>, 1024};
-    return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, STAGE, 256>, 256};
-}
+// Small scenes (all planes in shared memory, several CTAs per SM): per-thread shadow walk, 256 threads.
+// Large scenes: warp-cooperative shadow rays; one CTA of 1024 threads per SM once the endpoint plane
+// takes more than half of shared memory.
 template <int BANDS, bool COUNT, bool HITS>
-KernelChoice pick_stage(int stage, bool big) {
-    switch (stage) {
-        case 0: return pick_maxt<BANDS, COUNT, HITS, 0>(big);
-        case 1: return pick_maxt<BANDS, COUNT, HITS, 1>(big);
-        default: return pick_maxt<BANDS, COUNT, HITS, 2>(big);
+KernelChoice pick_kernel(int stage, bool big_block, bool coop) {
+    if (stage == 0) {
+        if (coop) return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 0, 256, true>, 256};
+        return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 0, 256, false>, 256};
     }
+    if (stage == 1) {
+        if (big_block) return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 1, 1024, true>, 1024};
+        return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 1, 256, true>, 256};
+    }
+    return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 2, 256, true>, 256};
 }
 template <int BANDS>
-KernelChoice pick_mode(bool count, bool hits, int stage, bool big) {
-    if (hits) return count ? pick_stage<BANDS, true, true>(stage, big) : pick_stage<BANDS, false, true>(stage, big);
-    return count ? pick_stage<BANDS, true, false>(stage, big) : pick_stage<BANDS, false, false>(stage, big);
+KernelChoice pick_mode(bool count, bool hits, int stage, bool big, bool coop) {
+    if (hits) return count ? pick_kernel<BANDS, true, true>(stage, big, coop) : pick_kernel<BANDS, false, true>(stage, big, coop);
+    return count ? pick_kernel<BANDS, true, false>(stage, big, coop) : pick_kernel<BANDS, false, false>(stage, big, coop);
 }
 
 }  // namespace
@@ -310,8 +373,9 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     // One CTA per SM once the planes take more than half of shared memory: use 1024 threads then.
     const bool big_block = smem > (size_t)dev.smem_optin / 2;
     const bool hits = a.hits != nullptr;
-    KernelChoice k = a.bands == 8 ? pick_mode<8>(count_tests, hits, stage, big_block)
-                                  : pick_mode<1>(count_tests, hits, stage, big_block);
+    const bool coop = stage != 0 || a.n_walls >= 128;
+    KernelChoice k = a.bands == 8 ? pick_mode<8>(count_tests, hits, stage, big_block, coop)
+                                  : pick_mode<1>(count_tests, hits, stage, big_block, coop);
 
     cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

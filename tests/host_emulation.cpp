@@ -23,7 +23,7 @@ struct HostScene {
 
 struct Hit { float t, e, x, y; uint32_t ray; uint16_t bounce, kind; };
 
-template <int BANDS>
+template <int BANDS, bool COUNT>
 void run(const HostScene &sc, const rar_trace_params &p, long long *hist, Hit *hits, long long cap, long long *count,
          rar::RayCounters &ctr) {
     rar::RayConsts c = rar::ray_consts(p);
@@ -34,7 +34,7 @@ void run(const HostScene &sc, const rar_trace_params &p, long long *hist, Hit *h
         rar::ray_init(r, (uint32_t)id, c);
         for (int i = 0; i < c.max_bounce_count; i++) {
             rar::Arrival<BANDS> a[2];
-            bool alive = rar::ray_bounce<BANDS, true>(sc, c, r, a[0], a[1], &ctr);
+            bool alive = rar::ray_bounce<BANDS, COUNT>(sc, c, r, a[0], a[1], &ctr);
             for (int k = 0; k < 2; k++) {
                 if (!a[k].has) continue;
                 if (hits) {
@@ -54,9 +54,8 @@ void run(const HostScene &sc, const rar_trace_params &p, long long *hist, Hit *h
 }
 }  // namespace
 
-extern "C" __attribute__((visibility("default")))
-int emu_trace(const rar_segment *walls, int n, const float *band_abs, const rar_trace_params *p, long long *hist,
-              void *hits, long long cap, long long *count, rar_counters *out) {
+static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const float *band_abs, const rar_trace_params *p,
+                          long long *hist, void *hits, long long cap, long long *count, rar_counters *out) {
     std::vector<rar::f4> g(n + 1), m0(n + 1);
     std::vector<rar::f2> m1(n + 1);
     rar::split_walls(walls, n, g.data(), m0.data(), m1.data());
@@ -64,15 +63,34 @@ int emu_trace(const rar_segment *walls, int n, const float *band_abs, const rar_
     rar::RayCounters ctr;
     std::memset(&ctr, 0, sizeof ctr);
     long long cnt = 0;
-    if (p->bands <= 1) run<1>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
-    else if (p->bands == 8) run<8>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
-    else return -5;
+    if (p->bands <= 1) {
+        if (counting) run<1, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else run<1, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+    } else if (p->bands == 8) {
+        if (counting) run<8, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else run<8, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+    } else {
+        return -5;
+    }
     if (count) *count = cnt;
     if (out) {
         out->ray_bounces = ctr.ray_bounces; out->nearest_tests = ctr.nearest_tests; out->shadow_tests = ctr.shadow_tests;
         out->direct_hits = ctr.direct_hits; out->nee_hits = ctr.nee_hits;
     }
     return 0;
+}
+
+// counting != 0: the instantiation that keeps the reference's test counters (always resolves the shadow ray);
+// counting == 0: the production instantiation (skips shadow rays whose estimate cannot clear the threshold).
+extern "C" __attribute__((visibility("default")))
+int emu_trace(const rar_segment *walls, int n, const float *band_abs, const rar_trace_params *p, long long *hist,
+              void *hits, long long cap, long long *count, rar_counters *out) {
+    return emu_trace_impl(true, walls, n, band_abs, p, hist, hits, cap, count, out);
+}
+extern "C" __attribute__((visibility("default")))
+int emu_trace_nocount(const rar_segment *walls, int n, const float *band_abs, const rar_trace_params *p, long long *hist,
+                      void *hits, long long cap, long long *count, rar_counters *out) {
+    return emu_trace_impl(false, walls, n, band_abs, p, hist, hits, cap, count, out);
 }
 
 // ---- FFT / partitioned overlap-save convolution: the same index logic as conv_kernels.cu ----------------

@@ -22,6 +22,9 @@ def _check(O, sc, kw):
     assert np.array_equal(hist, r.hist)
     assert len(hits) == len(r.hits) and hits.tobytes() == r.hits.tobytes()
     assert ctr == r.counters
+    # the production instantiation (no counters: shadow rays below the deposit threshold are skipped)
+    hist2, hits2, _ = emulation.trace(O, sc.walls, P, ba, counting=False)
+    assert np.array_equal(hist2, r.hist) and hits2.tobytes() == r.hits.tobytes()
     return r
 
 
