@@ -354,45 +354,60 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     if (n_rays <= 0 || a.p.max_bounce_count <= 0) return cudaSuccess;
     if (a.bands != 1 && a.bands != 8) return cudaErrorInvalidValue;
 
-    // Staging mode by shared-memory footprint (16-byte barrier slot + planes).
+    // Candidate configurations, by shared-memory footprint (16-byte barrier slot + planes):
+    //   stage 0 / 256 threads : all three planes on chip;
+    //   stage 1 / 256 threads : endpoint plane on chip, materials read through L1 once per bounce;
+    //   stage 1 / 1024 threads: one CTA per SM when the endpoint plane needs most of shared memory;
+    //   stage 2 / 256 threads : planes too large for shared memory, broadcast loads served by L1/L2
+    //                           (measured as fast per test as the staged path: the loads are broadcast
+    //                           and 32 resident warps hide their latency).
+    // The one that keeps the most threads resident per SM wins (ties: lower stage).
     const size_t geo_bytes = (size_t)a.n_walls * 16;
     const size_t m1_bytes = ((size_t)a.n_walls * 8 + 15) & ~(size_t)15;
     const size_t budget = (size_t)dev.smem_optin - 1024;
-    int stage;
-    size_t smem;
-    if (16 + 2 * geo_bytes + m1_bytes <= budget && 16 + 2 * geo_bytes + m1_bytes <= 96 * 1024) {
-        stage = 0;  // small scenes: everything on chip, several CTAs per SM still fit
-        smem = 16 + 2 * geo_bytes + m1_bytes;
-    } else if (16 + geo_bytes <= budget) {
-        stage = 1;
-        smem = 16 + geo_bytes;
-    } else {
-        stage = 2;
-        smem = 16;
-    }
-    // One CTA per SM once the planes take more than half of shared memory: use 1024 threads then.
-    const bool big_block = smem > (size_t)dev.smem_optin / 2;
     const bool hits = a.hits != nullptr;
-    const bool coop = stage != 0 || a.n_walls >= 128;
-    KernelChoice k = a.bands == 8 ? pick_mode<8>(count_tests, hits, stage, big_block, coop)
-                                  : pick_mode<1>(count_tests, hits, stage, big_block, coop);
-
-    cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    struct Cand { int stage; bool big; size_t smem; };
+    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes}, {1, false, 16 + geo_bytes}, {1, true, 16 + geo_bytes}, {2, false, 16}};
+    KernelChoice k{nullptr, 0};
+    size_t smem = 0;
+    bool big_block = false;
+    int best_resident = -1, per_sm = 0;
+    for (const Cand &c : cands) {
+        if (c.smem > budget) continue;
+        const bool coop = c.stage != 0 || a.n_walls >= 128;
+        KernelChoice kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, c.stage, c.big, coop)
+                                       : pick_mode<1>(count_tests, hits, c.stage, c.big, coop);
+        cudaError_t e = cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        int blocks = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kc.fn, kc.max_threads, c.smem);
+        if (e != cudaSuccess) return e;
+        const int resident = blocks * kc.max_threads;
+        if (resident > best_resident) {
+            best_resident = resident;
+            k = kc;
+            smem = c.smem;
+            big_block = c.big;
+            per_sm = blocks;
+        }
+    }
+    if (best_resident <= 0) return cudaErrorLaunchOutOfResources;
 
     // Block size: large enough to amortise the staging, small enough that small dispatches still
     // cover the machine (config 1 traces only 15 040 rays).
     int threads = k.max_threads;
     if (!big_block) {
         while (threads > 64 && (n_rays + threads - 1) / threads < 2LL * dev.sm_count) threads >>= 1;
+        if (threads != k.max_threads) {
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, threads, smem);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        }
     }
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, threads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     long long want = (n_rays + threads - 1) / threads;
     long long cap = (long long)per_sm * dev.sm_count;
     int grid = (int)(want < cap ? want : cap);
+    cudaError_t e;
 
     TraceLaunch arg = a;
     void *params[] = {&arg};

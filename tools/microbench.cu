@@ -1,0 +1,101 @@
+// microbench.cu -- issue-rate micro-peaks on the device, used to choose the roofline denominator of the
+// ray stage (SURVEY.md 8d asks for measured FFMA / shared-memory-broadcast peaks).  Standalone:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/microbench tools/microbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITER 4096
+
+// mode 0: FFMA with immediate multiplier/addend; 1: FFMA with three register operands;
+// 2: FMUL reg; 3: FADD reg; 4: FFMA reg + FADD reg interleaved; 5: FFMA reg + FSETP interleaved
+template <int MODE>
+__global__ void __launch_bounds__(256) k(float *out, const float *in) {
+    float a = in[0], b = in[1], c2 = in[2], d = in[3];
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = threadIdx.x * 1e-3f + j;
+    int cnt = 0;
+    for (int i = 0; i < ITER; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (MODE == 0) x[j] = __fmaf_rn(x[j], 0.999f, 1e-4f);
+                if (MODE == 1) x[j] = __fmaf_rn(x[j], a, b);
+                if (MODE == 2) x[j] = __fmul_rn(x[j], a);
+                if (MODE == 3) x[j] = __fadd_rn(x[j], b);
+                if (MODE == 4) { x[j] = (j & 1) ? __fmaf_rn(x[j], a, b) : __fadd_rn(x[j], c2); }
+                if (MODE == 5) { x[j] = __fmaf_rn(x[j], a, b); cnt += (x[j] > d) ? 1 : 0; }
+            }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += x[j];
+    if (s == 12345.678f || cnt == -1) out[0] = s;
+}
+
+// shared-memory broadcast LDS.128 rate: every lane reads the same 16 bytes
+__global__ void __launch_bounds__(256) lds_bcast(float *out, int n) {
+    __shared__ float4 buf[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) buf[i] = make_float4(i, 1, 2, 3);
+    __syncthreads();
+    float s = 0;
+    for (int i = 0; i < ITER; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            float4 v = buf[(i * 16 + u + n) & 1023];
+            s += v.x + v.w;
+        }
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <class F>
+double time_ms(F f) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    f();
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        f();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    int sms = p.multiProcessorCount, blocks = sms * 8;
+    float *out, *in;
+    cudaMalloc(&out, 64);
+    cudaMalloc(&in, 64);
+    float h[4] = {0.999f, 1e-4f, 1e-5f, 1e30f};
+    cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
+    const double ops = (double)blocks * 256 * ITER * 32.0;
+    const char *names[] = {"FFMA imm-form", "FFMA 3-register", "FMUL register", "FADD register", "FFMA+FADD 1:1", "FFMA+FSETP+IADD"};
+    double ms[6];
+    ms[0] = time_ms([&] { k<0><<<blocks, 256>>>(out, in); });
+    ms[1] = time_ms([&] { k<1><<<blocks, 256>>>(out, in); });
+    ms[2] = time_ms([&] { k<2><<<blocks, 256>>>(out, in); });
+    ms[3] = time_ms([&] { k<3><<<blocks, 256>>>(out, in); });
+    ms[4] = time_ms([&] { k<4><<<blocks, 256>>>(out, in); });
+    ms[5] = time_ms([&] { k<5><<<blocks, 256>>>(out, in); });
+    printf("device %s, %d SMs\n", p.name, sms);
+    for (int m = 0; m < 6; m++)
+        printf("%-18s %8.3f ms  %7.2f T lane-ops/s  (%.3f warp-inst/clk/SMSP at 1.965 GHz)\n", names[m], ms[m],
+               ops / (ms[m] * 1e-3) / 1e12, ops / 32.0 / (ms[m] * 1e-3) / (sms * 4 * 1.965e9));
+    double l = time_ms([&] { lds_bcast<<<blocks, 256>>>(out, 3); });
+    const double lds = (double)blocks * 256 * ITER * 16.0;
+    printf("LDS.128 broadcast  %8.3f ms  %7.2f T lane-loads/s  (%.3f warp-LDS/clk/SM)\n", l, lds / (l * 1e-3) / 1e12,
+           lds / 32.0 / (l * 1e-3) / (sms * 1.965e9));
+    return 0;
+}

@@ -31,6 +31,10 @@ def main():
         return
     if what == "c2":
         sc, bands = scenes.shoebox(), 1
+    elif what == "c1":
+        sc, bands = scenes.smoll_room(), 1
+    elif what.startswith("walls"):          # e.g. walls16000: staging-mode comparison at a given wall count
+        sc, bands = scenes.maze(n_segments=int(what[5:]), ray_count=148 * 1024 * 2, max_bounces=8, bands=8), 1
     else:
         sc, bands = scenes.maze(n_segments=10000, ray_count=148 * 1024 * 2, max_bounces=16, bands=8), (8 if what == "maze8" else 1)
     n = sc.impulse_length
@@ -46,6 +50,12 @@ def main():
         ctx.trace(p, 0)
         ctx.sync()
         print(f"{what} trace {1e3 * (time.perf_counter() - t0):.3f} ms")
+    ctx.get_counters(reset=True)
+    p.flags = _capi.RAR_FLAG_COUNT_TESTS
+    ctx.ir_clear(0, n, bands)
+    ctx.trace(p, 0)
+    c = ctx.get_counters()
+    print("tests per launch", c["nearest_tests"] + c["shadow_tests"], c)
     print("nonzero bins", int(np.count_nonzero(ctx.ir_read_fixed(0, n * bands))))
 
 
