@@ -250,7 +250,6 @@ def run_ours(args):
         e2e_step(f)
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks
     tt = torch.tensor([ms, e2e_s * 1e3, float(tests_total)], dtype=torch.float64, device=dev)
@@ -274,9 +273,15 @@ def run_ours(args):
     except Exception as ex:  # keep the headline even if a secondary leg fails
         extra["maze"] = {"error": str(ex)}
     try:
+        extra["config1"] = bench_config1(ctx, _capi, scenes, torch, stream)
+    except Exception as ex:
+        extra["config1"] = {"error": str(ex)}
+    try:
         extra["conv"] = bench_conv(ctx, _capi, scenes, torch, stream, dev, peaks, peaks_kind, args, world, dist)
     except Exception as ex:
         extra["conv"] = {"error": str(ex)}
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the timed region and the secondary legs
 
     cpu = None
     if rank == 0 and world == 1:
@@ -358,6 +363,46 @@ def bench_maze(ctx, _capi, scenes, torch, stream, flush):
         out[f"bands{bands}"] = {"tests": tests, "ms": best, "tests_per_s": tests / (best * 1e-3)}
     out["workload"] = f"config3 geometry: 10000-wall maze, {sc.ray_count} rays x 16 bounces (reduced ray count)"
     return out
+
+
+def bench_config1(ctx, _capi, scenes, torch, stream):
+    """Config 1, the reference's own real-time case: bundled SmollRoom, 15 000 rays x 5 bounces per frame,
+    a 0.1 s chunk (4800 samples) convolved with the 1.5 s IR (72 000 taps) through the host-buffer API, and the
+    whole 42 624-sample clip in one call (BakeAudio)."""
+    sc = scenes.smoll_room()
+    n = sc.impulse_length
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(3, n, 1)
+
+    def prm(frame):
+        return _capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
+                                       sc.max_bounces, frame, sc.ray_count, 100, sc.sample_rate, n)
+    for f in range(3):
+        ctx.trace(prm(f + 1), 3)
+    torch.cuda.synchronize()
+    reps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for f in range(reps):
+        ctx.trace(prm(10 + f), 3)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    frame_ms = e0.elapsed_time(e1) / reps
+    clip = scenes.synthetic_clip()
+    chunk = clip[:4800]
+    ctx.convolve(3, chunk, reps + 3, n)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.convolve(3, chunk, reps + 3, n)
+    chunk_ms = (time.perf_counter() - t0) / 20 * 1e3
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx.convolve(3, clip, reps + 3, n)
+    clip_ms = (time.perf_counter() - t0) / 10 * 1e3
+    return {"workload": "config1: SmollRoom 20 walls, 15000 rays x 5 bounces per frame; 1.5 s IR; 4800-sample chunk / 42624-sample clip",
+            "ir_build_ms_per_frame": frame_ms, "tests_per_frame": 2572899, "tests_per_s": 2572899 / (frame_ms * 1e-3),
+            "chunk_convolve_e2e_ms": chunk_ms, "chunk_realtime_factor": 100.0 / chunk_ms,
+            "clip_convolve_e2e_ms": clip_ms, "clip_samples_per_s": (len(clip) + n) / (clip_ms * 1e-3)}
 
 
 def bench_conv(ctx, _capi, scenes, torch, stream, dev, peaks, peaks_kind, args, world, dist):
