@@ -141,7 +141,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_ours(args):
@@ -326,7 +326,7 @@ def run_ours(args):
             "peaks": {"kind": peaks_kind, "hbm_gbs": peaks.get("hbm_gbs"), "fp32_laneops_per_s_measured": fp32_peak},
         }
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -454,7 +454,30 @@ def bench_conv(ctx, _capi, scenes, torch, stream, dev, peaks, peaks_kind, args, 
     }
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL: "NCCL version ...") write to fd 1 from C.  The contract is ONE JSON line on stdout, so
+    everything else is sent to stderr and the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
