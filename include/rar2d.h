@@ -78,7 +78,11 @@ typedef struct rar_hit_key {
 #define RAR_FLAG_EXACT_RAY_COUNT 1u /* trace exactly ray_count rays; default reproduces the reference's
                                        unguarded dispatch of ceil(rayCount/64)*64 threads
                                        (Raytrace2D.compute:49-52, Helpers/ComputeHelper.cs:27-31) */
-#define RAR_FLAG_COUNT_TESTS 2u     /* also count ray-segment tests (slower; for measurement and parity) */
+#define RAR_FLAG_COUNT_TESTS 2u     /* also count ray-segment tests the way the reference performs them
+                                       (slower; for measurement and parity) */
+#define RAR_FLAG_COUNT_EXECUTED 4u  /* with COUNT_TESTS: count only the tests the production kernel evaluates
+                                       (it skips shadow rays whose estimate cannot clear the 1e-5 threshold of
+                                       Raytrace2D.compute:111); used for the roofline's achieved figure */
 
 /* The uniforms of Trace and ProcessHits: Raytrace2D.compute:5-10,36 set at RayTraceManager.cs:191-201
  * and :227-228; ImpulseLength from RayTraceManager.cs:174.  `bands`/`time_divisor` carry the banded

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librar2d.so")
 RAR_OK = 0
 RAR_FLAG_EXACT_RAY_COUNT = 1
 RAR_FLAG_COUNT_TESTS = 2
+RAR_FLAG_COUNT_EXECUTED = 4
 
 # include/rar2d.h rar_segment / rar_ray_info / rar_hit_key
 SEGMENT_DTYPE = np.dtype(

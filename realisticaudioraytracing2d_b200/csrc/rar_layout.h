@@ -39,6 +39,7 @@ inline RayConsts ray_consts(const rar_trace_params &p) {
     c.sample_rate = p.sample_rate;
     c.impulse_length = p.impulse_length;
     c.time_divisor = p.time_divisor;
+    c.count_executed = (p.flags & RAR_FLAG_COUNT_EXECUTED) ? 1 : 0;
     return c;
 }
 

@@ -36,6 +36,7 @@ struct RayConsts {
     int ray_count;
     int sample_rate, impulse_length;
     float time_divisor;
+    int count_executed;  // with COUNT: resolve (and count) only the shadow rays the production kernel resolves
 };
 
 struct RayCounters {
@@ -306,7 +307,7 @@ RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r
         c.inv = rar_rcp(total * total);
         c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
         c.nee_candidate = c.nee_e > 1e-5f;
-        c.want_shadow = COUNT ? 1 : c.nee_candidate;
+        c.want_shadow = (COUNT && !p.count_executed) ? 1 : c.nee_candidate;
         if (c.want_shadow) {
             c.shadow = make_shadow_ray(rar_fma(wnx, kEps, r.px), rar_fma(wny, kEps, r.py), p.listener_x, p.listener_y, dl);
             c.nee_t = r.time + rar_div(dl, p.speed_of_sound);

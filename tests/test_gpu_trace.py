@@ -212,3 +212,23 @@ def test_batched_listeners_config4_shape(ctx, oracle):
     for l, (lx, ly) in enumerate(listeners):
         want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, listener=(float(lx), float(ly))))).hist
         assert np.array_equal(ctx.ir_read_fixed(10 + l, 24000), want), l
+
+
+def test_executed_test_count_is_a_subset_and_result_is_unchanged(ctx, oracle):
+    """RAR_FLAG_COUNT_EXECUTED counts what the production kernel evaluates: never more shadow tests than the
+    reference performs, the same nearest tests, and the same histogram."""
+    sc = scenes.shoebox(ray_count=65536, max_bounces=32)
+    kw = trace_kwargs(sc)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    res = {}
+    for name, flags in (("ref", _capi.RAR_FLAG_COUNT_TESTS), ("exe", _capi.RAR_FLAG_COUNT_TESTS | _capi.RAR_FLAG_COUNT_EXECUTED), ("prod", 0)):
+        ctx.ir_clear(0, n, 1)
+        ctx.get_counters(reset=True)
+        ctx.trace(capi_params(_capi, dict(kw, flags=flags)), 0)
+        res[name] = (ctx.ir_read_fixed(0, n), ctx.get_counters())
+    assert np.array_equal(res["ref"][0], res["exe"][0]) and np.array_equal(res["ref"][0], res["prod"][0])
+    r, e = res["ref"][1], res["exe"][1]
+    assert e["nearest_tests"] == r["nearest_tests"] and e["nee_hits"] == r["nee_hits"] and e["direct_hits"] == r["direct_hits"]
+    assert 0 < e["shadow_tests"] < r["shadow_tests"]
+    assert res["prod"][1]["nearest_tests"] == 0                     # no counting without the flag
