@@ -242,10 +242,12 @@ struct BounceCtx {
     float band_keep[BANDS > 1 ? BANDS : 1];
 };
 
-// Returns false when the ray ended without hitting a wall (:86-90).
+// Returns false when the ray ended without hitting a wall (:86-90).  dbg: where to record this bounce's
+// vertex for the debugRays buffer, or nullptr; dbg_flags bit 0: record wall hits (:96-97, thread id < 100),
+// bit 1: record the escape vertex (:87-88, thread id < debugRayCount).
 template <int BANDS, bool COUNT, class Scene>
 RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
-                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg_hit = nullptr, f4 *dbg_miss = nullptr) {
+                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
     direct.has = 0;
     c.want_shadow = 0;
     c.nee_candidate = 0;
@@ -274,7 +276,7 @@ RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r
         }
     }
     if (c.hit < 0) {  // :86-90
-        if (dbg_miss) *dbg_miss = f4{rar_fma(r.dx, 20.0f, r.px), rar_fma(r.dy, 20.0f, r.py), 0.0f, 0.0f};
+        if (dbg && (dbg_flags & 2)) *dbg = f4{rar_fma(r.dx, 20.0f, r.px), rar_fma(r.dy, 20.0f, r.py), 0.0f, 0.0f};
         return false;
     }
 
@@ -282,7 +284,7 @@ RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r
     r.py = rar_fma(r.dy, closest, r.py);
     r.time += rar_div(closest, r.speed);
     r.dist += closest;
-    if (dbg_hit) *dbg_hit = f4{r.px, r.py, r.energy, 0.0f};  // :96-97
+    if (dbg && (dbg_flags & 1)) *dbg = f4{r.px, r.py, r.energy, 0.0f};  // :96-97
 
     c.m0 = sc.mat0(c.hit);  // :99
     c.m1 = sc.mat1(c.hit);
@@ -409,10 +411,10 @@ RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &
 // The three phases with a per-thread shadow walk: what a single thread of the reference does.
 template <int BANDS, bool COUNT, class Scene>
 RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
-                       Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg_hit = nullptr, f4 *dbg_miss = nullptr) {
+                       Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
     BounceCtx<BANDS> c;
     nee.has = 0;
-    if (!bounce_begin<BANDS, COUNT>(sc, p, r, direct, c, ctr, dbg_hit, dbg_miss)) return false;
+    if (!bounce_begin<BANDS, COUNT>(sc, p, r, direct, c, ctr, dbg, dbg_flags)) return false;
     bool visible = true;
     if (c.want_shadow) {
         int tests = 0;

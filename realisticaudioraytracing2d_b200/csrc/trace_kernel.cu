@@ -245,15 +245,16 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
         RayState<BANDS> r;
         if (alive) ray_init(r, id, a.p);
 
+        // debugRays (Raytrace2D.compute:63,87,96): thread ids < 100 record wall hits (hard-coded in the shader),
+        // ids < debugRayCount record the escape vertex.
         f4 *dbg = nullptr;
-        bool dbg100 = false, dbgN = false;
+        int dbg_flags = 0;
         if (a.debug_rays != nullptr && alive) {
             const long long row = (long long)id * (max_b + 1);
-            if (row + max_b < a.debug_capacity) {
+            dbg_flags = (id < 100u ? 1 : 0) | (id < (uint32_t)a.debug_ray_count ? 2 : 0);
+            if (dbg_flags && row + max_b < a.debug_capacity) {
                 dbg = a.debug_rays + row;
-                dbg100 = id < 100u;                          // Raytrace2D.compute:63,96 (hard-coded 100)
-                dbgN = id < (uint32_t)a.debug_ray_count;     // :87
-                if (dbg100) dbg[0] = f4{r.px, r.py, r.energy, 0.0f};
+                if (dbg_flags & 1) dbg[0] = f4{r.px, r.py, r.energy, 0.0f};
             }
         }
 
@@ -267,8 +268,7 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
             c.shadow = ShadowRay{0.f, 0.f, 0.f, 0.f, 0.f};
             bool hit_wall = false;
             if (alive) {
-                hit_wall = bounce_begin<BANDS, COUNT>(sc, a.p, r, direct, c, &ctr, dbg100 ? dbg + i + 1 : nullptr,
-                                                      dbgN ? dbg + i + 1 : nullptr);
+                hit_wall = bounce_begin<BANDS, COUNT>(sc, a.p, r, direct, c, &ctr, dbg ? dbg + i + 1 : nullptr, dbg_flags);
             }
             const bool pending = hit_wall && c.want_shadow;
             bool visible = true;

@@ -23,6 +23,9 @@ def oracle():
 def ctx():
     """One CUDA context of the product library for the GPU tests."""
     from realisticaudioraytracing2d_b200 import _capi
+    if not os.path.exists(_capi.LIB_PATH):      # normally built by __graft_entry__.build(); nvcc is on the box too
+        from realisticaudioraytracing2d_b200 import build as _b
+        _b.build()
     c = _capi.Context(0)
     yield c
     c.destroy()
