@@ -186,8 +186,12 @@ RAR_API int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t 
 
 /* BASELINE config 4 (batched auralisation): the same dispatch traced for n_listeners listener positions
  * (listeners_xy = x0,y0,x1,y1,...; params->listener_pos is ignored); listener l accumulates into slot
- * first_slot + l, each of which must be configured like `slot` of rar_trace.  Equivalent to n_listeners
- * calls of rar_trace.  Asynchronous.  Listeners shard across GPUs by contiguous range with no exchange. */
+ * first_slot + l, each of which must be configured like `slot` of rar_trace.  The result in every slot is
+ * identical to a single-listener rar_trace; for broadband slots the work is fused: a ray's path does not depend on
+ * the listener (it is tested, never hit: Raytrace2D.compute:74-84,101-119), so each ray is traced once and only the
+ * listener crossing / next-event tests run per listener.  With RAR_FLAG_COUNT_TESTS the counters then hold the tests
+ * executed (nearest-hit tests once per ray, not once per listener).  Asynchronous after an initial upload.
+ * Listeners shard across GPUs by contiguous range with no exchange. */
 RAR_API int rar_trace_listeners(rar_context *ctx, const rar_trace_params *params, const float *listeners_xy,
                                 int32_t n_listeners, int32_t first_slot);
 

@@ -110,6 +110,8 @@ struct rar_context {
     DevBuf<f4> d_debug;
     int debug_entries = 0;
     DevBuf<float> d_irf;  // float view of a slot (scratch)
+    DevBuf<f2> d_listeners;                        // batched-listener launch arguments
+    DevBuf<unsigned long long *> d_listener_hists;
     std::vector<Ticket *> tickets;
     std::vector<rar_convolver *> convolvers;
 };
@@ -295,6 +297,8 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_counters.release();
     ctx->d_debug.release();
     ctx->d_irf.release();
+    ctx->d_listeners.release();
+    ctx->d_listener_hists.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RAR_OK;
@@ -479,13 +483,48 @@ int rar_trace_listeners(rar_context *ctx, const rar_trace_params *params, const 
     if (!params) return fail(ctx, RAR_ERR_INVALID, "null params");
     if (n_listeners < 0 || (n_listeners > 0 && !listeners_xy)) return fail(ctx, RAR_ERR_INVALID, "bad listener array");
     if (first_slot < 0 || (long long)first_slot + n_listeners > kMaxSlots) return fail(ctx, RAR_ERR_INVALID, "slot range out of bounds");
-    for (int l = 0; l < n_listeners; l++) {
-        rar_trace_params p = *params;
-        p.listener_pos[0] = listeners_xy[2 * l];
-        p.listener_pos[1] = listeners_xy[2 * l + 1];
-        int rc = rar_trace(ctx, &p, first_slot + l);
-        if (rc != RAR_OK) return rc;
+    if (n_listeners == 0) return RAR_OK;
+    if (n_listeners == 1 || params->bands != 1) {
+        // one listener, or banded slots: plain single-listener traces
+        for (int l = 0; l < n_listeners; l++) {
+            rar_trace_params p = *params;
+            p.listener_pos[0] = listeners_xy[2 * l];
+            p.listener_pos[1] = listeners_xy[2 * l + 1];
+            int rc = rar_trace(ctx, &p, first_slot + l);
+            if (rc != RAR_OK) return rc;
+        }
+        return RAR_OK;
     }
+    // Fused kernel: every ray is traced once and tested against all listeners.
+    int rc = check_trace_params(ctx, params);
+    if (rc != RAR_OK) return rc;
+    std::vector<unsigned long long *> hists(n_listeners);
+    std::vector<f2> pos(n_listeners);
+    for (int l = 0; l < n_listeners; l++) {
+        Slot *S = get_slot(ctx, first_slot + l, false);
+        if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "a listener slot is not configured (call rar_ir_clear first)");
+        if (S->impulse_length != params->impulse_length || S->bands != 1)
+            return fail(ctx, RAR_ERR_INVALID, "params impulse_length/bands do not match a listener slot");
+        hists[l] = reinterpret_cast<unsigned long long *>(S->d_hist);
+        pos[l] = f2{listeners_xy[2 * l], listeners_xy[2 * l + 1]};
+        S->H_valid = false;
+    }
+    RAR_CUDA(ctx, ctx->d_listeners.reserve((size_t)n_listeners));
+    RAR_CUDA(ctx, ctx->d_listener_hists.reserve((size_t)n_listeners));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners.p, pos.data(), (size_t)n_listeners * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_listener_hists.p, hists.data(), (size_t)n_listeners * sizeof(unsigned long long *),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors are pageable
+    TraceLaunch a;
+    fill_launch(ctx, params, a);
+    a.listeners = ctx->d_listeners.p;
+    a.listener_hists = ctx->d_listener_hists.p;
+    a.n_listeners = n_listeners;
+    const bool count = (params->flags & RAR_FLAG_COUNT_TESTS) != 0;
+    a.counters = count ? ctx->d_counters.p : nullptr;
+    int launched = 0;
+    RAR_CUDA(ctx, launch_trace(a, count, ctx->dev, ctx->stream, &launched));
+    ctx->launches += launched;
     return RAR_OK;
 }
 

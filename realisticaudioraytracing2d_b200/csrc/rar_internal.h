@@ -28,6 +28,11 @@ struct TraceLaunch {
     f4 *debug_rays;                // max(100, debug_ray_count) * (max_bounce_count+1) or nullptr
     int debug_ray_count;
     int debug_capacity;            // entries in debug_rays
+    // batched listeners (BASELINE config 4): n_listeners > 0 selects the fused kernel; listener l deposits
+    // into listener_hists[l]
+    const f2 *listeners;
+    unsigned long long *const *listener_hists;
+    int n_listeners;
 };
 
 struct DeviceFacts {

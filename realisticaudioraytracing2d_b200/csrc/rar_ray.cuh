@@ -232,6 +232,7 @@ RAR_HD bool check_vis(const Scene &sc, const ShadowRay &q, int *tests) {
 template <int BANDS>
 struct BounceCtx {
     int hit;            // wall index, -1: ray left the scene
+    float closest;      // distance to it
     int want_shadow;    // the shadow ray must be resolved
     int nee_candidate;  // contribution clears the threshold (deposit iff visible)
     ShadowRay shadow;
@@ -242,90 +243,106 @@ struct BounceCtx {
     float band_keep[BANDS > 1 ? BANDS : 1];
 };
 
-// Returns false when the ray ended without hitting a wall (:86-90).  dbg: where to record this bounce's
-// vertex for the debugRays buffer, or nullptr; dbg_flags bit 0: record wall hits (:96-97, thread id < 100),
-// bit 1: record the escape vertex (:87-88, thread id < debugRayCount).
+// The pieces below are independent of the listener (nearest, advance, scatter) or take one listener
+// position (direct crossing, next-event estimate).  The ray's path never depends on the listener -- it is
+// tested but never hit (Raytrace2D.compute:74-84,101-119) -- which is what lets the batched-listener kernel
+// (BASELINE config 4) trace each ray once and run only the per-listener pieces for every listener.
+
+// :69-72
 template <int BANDS, bool COUNT, class Scene>
-RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
-                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
-    direct.has = 0;
-    c.want_shadow = 0;
-    c.nee_candidate = 0;
-    float closest;
-    nearest_hit(sc, r.px, r.py, r.dx, r.dy, closest, c.hit);  // :69-72
+RAR_HD void bounce_nearest(const Scene &sc, const RayState<BANDS> &r, BounceCtx<BANDS> &c, RayCounters *ctr) {
+    nearest_hit(sc, r.px, r.py, r.dx, r.dy, c.closest, c.hit);
     if (COUNT) {
         ctr->ray_bounces += 1;
         ctr->nearest_tests += (unsigned long long)sc.n_walls();
     }
+}
 
-    if (r.wall_depth == 0) {  // :74-84
-        float dl = intersect_circle(r.px, r.py, r.dx, r.dy, p.listener_x, p.listener_y, p.listener_radius);
-        if (dl < closest && dl < kInf) {
-            direct.has = 1;
-            direct.hx = rar_fma(r.dx, dl, r.px);
-            direct.hy = rar_fma(r.dy, dl, r.py);
-            direct.t = r.time + rar_div(dl, r.speed);
-            float total = r.dist + dl;
-            float denom = fmaxf(1.0f, total * total);
-            direct.e = rar_div(r.energy, denom);
-            if (BANDS > 1) {
+// :74-84: does the ray cross the listener circle at (lx, ly) before the wall?  Uses the state BEFORE the advance.
+template <int BANDS, bool COUNT>
+RAR_HD void listener_direct(const RayConsts &p, float lx, float ly, const RayState<BANDS> &r, float closest,
+                            Arrival<BANDS> &direct, RayCounters *ctr) {
+    direct.has = 0;
+    if (r.wall_depth != 0) return;
+    float dl = intersect_circle(r.px, r.py, r.dx, r.dy, lx, ly, p.listener_radius);
+    if (dl < closest && dl < kInf) {
+        direct.has = 1;
+        direct.hx = rar_fma(r.dx, dl, r.px);
+        direct.hy = rar_fma(r.dy, dl, r.py);
+        direct.t = r.time + rar_div(dl, r.speed);
+        float total = r.dist + dl;
+        float denom = fmaxf(1.0f, total * total);
+        direct.e = rar_div(r.energy, denom);
+        if (BANDS > 1) {
 #pragma unroll
-                for (int b = 0; b < BANDS; b++) direct.band_e[b] = rar_div(r.band_e[b], denom);
-            }
-            if (COUNT) ctr->direct_hits += 1;
+            for (int b = 0; b < BANDS; b++) direct.band_e[b] = rar_div(r.band_e[b], denom);
         }
+        if (COUNT) ctr->direct_hits += 1;
     }
+}
+
+// :86-99: end the ray if nothing was hit, else move it to the wall and fetch the wall's material.
+// dbg: where to record this bounce's vertex for the debugRays buffer, or nullptr; dbg_flags bit 0: record
+// wall hits (:96-97, thread id < 100), bit 1: record the escape vertex (:87-88, thread id < debugRayCount).
+template <int BANDS, class Scene>
+RAR_HD bool bounce_advance(const Scene &sc, RayState<BANDS> &r, BounceCtx<BANDS> &c, f4 *dbg, int dbg_flags) {
     if (c.hit < 0) {  // :86-90
         if (dbg && (dbg_flags & 2)) *dbg = f4{rar_fma(r.dx, 20.0f, r.px), rar_fma(r.dy, 20.0f, r.py), 0.0f, 0.0f};
         return false;
     }
-
-    r.px = rar_fma(r.dx, closest, r.px);  // :92-94
-    r.py = rar_fma(r.dy, closest, r.py);
-    r.time += rar_div(closest, r.speed);
-    r.dist += closest;
+    r.px = rar_fma(r.dx, c.closest, r.px);  // :92-94
+    r.py = rar_fma(r.dy, c.closest, r.py);
+    r.time += rar_div(c.closest, r.speed);
+    r.dist += c.closest;
     if (dbg && (dbg_flags & 1)) *dbg = f4{r.px, r.py, r.energy, 0.0f};  // :96-97
 
     c.m0 = sc.mat0(c.hit);  // :99
     c.m1 = sc.mat1(c.hit);
-    const float wnx = c.m0.x, wny = c.m0.y;
     c.keep = 1.0f - c.m0.z;
     if (BANDS > 1) {
         const float *ba = sc.band_abs(c.hit);
 #pragma unroll
         for (int b = 0; b < BANDS; b++) c.band_keep[b] = 1.0f - ba[b];
     }
-    c.dir_dot_n = dot2(r.dx, r.dy, wnx, wny);
-
-    if (r.wall_depth == 0) {  // :101-112
-        const float tlx = p.listener_x - r.px, tly = p.listener_y - r.py;
-        const float dl = rar_sqrt(dot2(tlx, tly, tlx, tly));
-        const bool flip = c.dir_dot_n > 0.0f;
-        const float enx = flip ? -wnx : wnx, eny = flip ? -wny : wny;
-        const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
-        const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
-        const float total = r.dist + dl;
-        c.geo = cos_t * 0.5f;
-        c.inv = rar_rcp(total * total);
-        c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
-        c.nee_candidate = c.nee_e > 1e-5f;
-        c.want_shadow = (COUNT && !p.count_executed) ? 1 : c.nee_candidate;
-        if (c.want_shadow) {
-            c.shadow = make_shadow_ray(rar_fma(wnx, kEps, r.px), rar_fma(wny, kEps, r.py), p.listener_x, p.listener_y, dl);
-            c.nee_t = r.time + rar_div(dl, p.speed_of_sound);
-        }
-    }
+    c.dir_dot_n = dot2(r.dx, r.dy, c.m0.x, c.m0.y);
     return true;
 }
 
-// `visible` is the outcome of the shadow phase (ignored unless c.want_shadow).  Returns false when the ray
-// ended (energy below 1e-3, :122).
-template <int BANDS, bool COUNT, class Scene>
-RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &nee,
-                          const BounceCtx<BANDS> &c, bool visible, RayCounters *ctr) {
-    (void)sc;
+// :101-112 for the listener at (lx, ly): the estimate's energy and arrival time, and the shadow ray that
+// decides it.  The reference evaluates checkVis before it knows whether the estimate clears the 1e-5
+// threshold (:111); checkVis has no side effect, so the contribution is computed first and the shadow ray
+// is requested only when the outcome can matter (with COUNT in reference mode it is always requested, so
+// that the test counters are the reference's).
+template <int BANDS, bool COUNT>
+RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<BANDS> &r, BounceCtx<BANDS> &c) {
+    c.want_shadow = 0;
+    c.nee_candidate = 0;
+    if (r.wall_depth != 0) return;
+    const float wnx = c.m0.x, wny = c.m0.y;
+    const float tlx = lx - r.px, tly = ly - r.py;
+    const float dl = rar_sqrt(dot2(tlx, tly, tlx, tly));
+    const bool flip = c.dir_dot_n > 0.0f;
+    const float enx = flip ? -wnx : wnx, eny = flip ? -wny : wny;
+    const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
+    const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
+    const float total = r.dist + dl;
+    c.geo = cos_t * 0.5f;
+    c.inv = rar_rcp(total * total);
+    c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
+    c.nee_candidate = c.nee_e > 1e-5f;
+    c.want_shadow = (COUNT && !p.count_executed) ? 1 : c.nee_candidate;
+    if (c.want_shadow) {
+        c.shadow = make_shadow_ray(rar_fma(wnx, kEps, r.px), rar_fma(wny, kEps, r.py), lx, ly, dl);
+        c.nee_t = r.time + rar_div(dl, p.speed_of_sound);
+    }
+}
+
+// :113-118: the estimate arrives iff it cleared the threshold and the listener is visible.
+template <int BANDS, bool COUNT>
+RAR_HD void nee_arrival(const RayState<BANDS> &r, const BounceCtx<BANDS> &c, bool visible, Arrival<BANDS> &nee,
+                        RayCounters *ctr) {
     nee.has = 0;
-    if (c.nee_candidate && visible) {  // :113-118
+    if (c.nee_candidate && visible) {
         nee.has = 1;
         nee.hx = r.px;
         nee.hy = r.py;
@@ -337,7 +354,11 @@ RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &
         }
         if (COUNT) ctr->nee_hits += 1;
     }
+}
 
+// :121-154: absorb, then transmit or reflect.  Returns false when the ray ended (energy below 1e-3, :122).
+template <int BANDS>
+RAR_HD bool bounce_scatter(const RayConsts &p, RayState<BANDS> &r, const BounceCtx<BANDS> &c) {
     r.energy *= c.keep;  // :121-122
     if (BANDS > 1) {
 #pragma unroll
@@ -406,6 +427,30 @@ RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &
     r.px = rar_fma(nx, kEps, r.px);
     r.py = rar_fma(ny, kEps, r.py);
     return true;
+}
+
+// Single-listener composition of the pieces, split around the shadow phase.
+// Returns false when the ray ended without hitting a wall (:86-90).
+template <int BANDS, bool COUNT, class Scene>
+RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
+                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
+    c.want_shadow = 0;
+    c.nee_candidate = 0;
+    bounce_nearest<BANDS, COUNT>(sc, r, c, ctr);
+    listener_direct<BANDS, COUNT>(p, p.listener_x, p.listener_y, r, c.closest, direct, ctr);
+    if (!bounce_advance(sc, r, c, dbg, dbg_flags)) return false;
+    listener_nee<BANDS, COUNT>(p, p.listener_x, p.listener_y, r, c);
+    return true;
+}
+
+// `visible` is the outcome of the shadow phase (ignored unless c.want_shadow).  Returns false when the ray
+// ended (energy below 1e-3, :122).
+template <int BANDS, bool COUNT, class Scene>
+RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &nee,
+                          const BounceCtx<BANDS> &c, bool visible, RayCounters *ctr) {
+    (void)sc;
+    nee_arrival<BANDS, COUNT>(r, c, visible, nee, ctr);
+    return bounce_scatter(p, r, c);
 }
 
 // The three phases with a per-thread shadow walk: what a single thread of the reference does.

@@ -109,7 +109,8 @@ __device__ __forceinline__ long long group_sum_q(unsigned peers, long long q) {
 }
 
 template <int BANDS>
-__device__ __forceinline__ void deposit_hist(const TraceLaunch &a, const Arrival<BANDS> &h, unsigned lane) {
+__device__ __forceinline__ void deposit_hist(const TraceLaunch &a, unsigned long long *hist, const Arrival<BANDS> &h,
+                                             unsigned lane) {
     int bin = -1;
     if (h.has) bin = time_bin(h.t, a.p.sample_rate, a.p.time_divisor, a.p.impulse_length);
     if (!__any_sync(kFull, bin >= 0)) return;
@@ -120,9 +121,9 @@ __device__ __forceinline__ void deposit_hist(const TraceLaunch &a, const Arrival
     if (BANDS == 1) {
         long long q = valid ? quantize_energy(h.e) : 0;
         if (shared_bin) q = group_sum_q(peers, q);
-        if (leader && q != 0) atomicAdd(a.hist + bin, (unsigned long long)q);
+        if (leader && q != 0) atomicAdd(hist + bin, (unsigned long long)q);
     } else {
-        unsigned long long *row = a.hist + (size_t)(valid ? bin : 0) * BANDS;
+        unsigned long long *row = hist + (size_t)(valid ? bin : 0) * BANDS;
 #pragma unroll
         for (int b = 0; b < BANDS; b++) {
             long long q = valid ? quantize_energy(h.band_e[b]) : 0;
@@ -194,11 +195,10 @@ __device__ __forceinline__ bool coop_shadow(const Scene &sc, bool pending, const
     return my_vis;
 }
 
-// ---- the kernel -------------------------------------------------------------------------------------
-
-template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP>
-__global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// Stages the wall planes into shared memory with 1-D TMA bulk copies (STAGE 0: all three planes, STAGE 1: the
+// endpoint plane) and returns the view the ray code reads.  All threads of the CTA call this once.
+template <int STAGE>
+__device__ __forceinline__ SceneView<STAGE> stage_scene(const TraceLaunch &a, unsigned char *smem_raw) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     f4 *s_geo = reinterpret_cast<f4 *>(smem_raw + 16);
     f4 *s_mat0 = s_geo + a.n_walls;
@@ -232,6 +232,15 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
     sc.ba = a.band_abs;
     sc.n = a.n_walls;
     sc.nb = a.bands;
+    return sc;
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+
+template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP>
+__global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const SceneView<STAGE> sc = stage_scene<STAGE>(a, smem_raw);
 
     const unsigned lane = threadIdx.x & 31u;
     const long long n_rays = a.ray_end - a.ray_begin;
@@ -286,9 +295,85 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
                 emit_hit(a, direct, id, i, 0);
                 emit_hit(a, nee, id, i, 1);
             } else {
-                deposit_hist(a, direct, lane);
-                deposit_hist(a, nee, lane);
+                deposit_hist(a, a.hist, direct, lane);
+                deposit_hist(a, a.hist, nee, lane);
             }
+        }
+    }
+
+    if (COUNT && a.counters != nullptr) {
+        unsigned long long v[5] = {ctr.ray_bounces, ctr.nearest_tests, ctr.shadow_tests, ctr.direct_hits, ctr.nee_hits};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            unsigned long long s = warp_sum_u64(v[k]);
+            if (lane == 0 && s != 0) atomicAdd(a.counters + k, s);
+        }
+    }
+}
+
+// ---- batched listeners (BASELINE config 4) ---------------------------------------------------------------
+//
+// The ray's path does not depend on the listener, so each ray is traced ONCE; per bounce the kernel runs the
+// nearest-hit loop once and then, for every listener, only the listener pieces: the direct crossing test
+// before the advance, and the next-event estimate with its shadow ray after it.  Listener l deposits into its
+// own histogram.  Result per listener: identical to a single-listener trace (same pieces, same order).
+template <bool COUNT, int STAGE, int MAXT, bool COOP>
+__global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_constant__ TraceLaunch a) {
+    constexpr int BANDS = 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const SceneView<STAGE> sc = stage_scene<STAGE>(a, smem_raw);
+
+    const unsigned lane = threadIdx.x & 31u;
+    const long long n_rays = a.ray_end - a.ray_begin;
+    const int max_b = a.p.max_bounce_count;
+    const int n_l = a.n_listeners;
+    RayCounters ctr = {0, 0, 0, 0, 0};
+
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_rays; base += (long long)gridDim.x * blockDim.x) {
+        const long long idx = base + threadIdx.x;
+        bool alive = idx < n_rays;
+        const uint32_t id = (uint32_t)(a.ray_begin + idx);
+        RayState<BANDS> r;
+        if (alive) ray_init(r, id, a.p);
+
+        for (int i = 0; i < max_b; i++) {
+            if (!__any_sync(kFull, alive)) break;
+            BounceCtx<BANDS> c;
+            c.hit = -1;
+            c.closest = kInf;
+            if (alive) bounce_nearest<BANDS, COUNT>(sc, r, c, &ctr);
+            __syncwarp();
+            for (int l = 0; l < n_l; l++) {  // direct crossings, state before the advance
+                const float2 lp = __ldg(reinterpret_cast<const float2 *>(a.listeners) + l);
+                Arrival<BANDS> direct;
+                direct.has = 0;
+                if (alive) listener_direct<BANDS, COUNT>(a.p, lp.x, lp.y, r, c.closest, direct, &ctr);
+                deposit_hist(a, a.listener_hists[l], direct, lane);
+            }
+            const bool hit_wall = alive && bounce_advance(sc, r, c, nullptr, 0);
+            for (int l = 0; l < n_l; l++) {  // next-event estimates from the hit point
+                const float2 lp = __ldg(reinterpret_cast<const float2 *>(a.listeners) + l);
+                c.want_shadow = 0;
+                c.nee_candidate = 0;
+                c.shadow = ShadowRay{0.f, 0.f, 0.f, 0.f, 0.f};
+                if (hit_wall) listener_nee<BANDS, COUNT>(a.p, lp.x, lp.y, r, c);
+                const bool pending = hit_wall && c.want_shadow;
+                bool visible = true;
+                if (COOP) {
+                    __syncwarp();
+                    visible = coop_shadow<COUNT>(sc, pending, c.shadow, lane, ctr);
+                } else if (pending) {
+                    int tests = 0;
+                    visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
+                    if (COUNT) ctr.shadow_tests += (unsigned long long)tests;
+                }
+                Arrival<BANDS> nee;
+                nee.has = 0;
+                if (hit_wall) nee_arrival<BANDS, COUNT>(r, c, visible, nee, &ctr);
+                __syncwarp();
+                deposit_hist(a, a.listener_hists[l], nee, lane);
+            }
+            if (alive) alive = hit_wall && bounce_scatter(a.p, r, c);
         }
     }
 
@@ -340,6 +425,18 @@ KernelChoice pick_kernel(int stage, bool big_block, bool coop) {
     }
     return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 2, 256, true>, 256};
 }
+template <bool COUNT>
+KernelChoice pick_listeners(int stage, bool big_block, bool coop) {
+    if (stage == 0) {
+        if (coop) return {(const void *)trace_listeners_kernel<COUNT, 0, 256, true>, 256};
+        return {(const void *)trace_listeners_kernel<COUNT, 0, 256, false>, 256};
+    }
+    if (stage == 1) {
+        if (big_block) return {(const void *)trace_listeners_kernel<COUNT, 1, 1024, true>, 1024};
+        return {(const void *)trace_listeners_kernel<COUNT, 1, 256, true>, 256};
+    }
+    return {(const void *)trace_listeners_kernel<COUNT, 2, 256, true>, 256};
+}
 template <int BANDS>
 KernelChoice pick_mode(bool count, bool hits, int stage, bool big, bool coop) {
     if (hits) return count ? pick_kernel<BANDS, true, true>(stage, big, coop) : pick_kernel<BANDS, false, true>(stage, big, coop);
@@ -353,6 +450,7 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     const long long n_rays = a.ray_end - a.ray_begin;
     if (n_rays <= 0 || a.p.max_bounce_count <= 0) return cudaSuccess;
     if (a.bands != 1 && a.bands != 8) return cudaErrorInvalidValue;
+    if (a.n_listeners > 0 && (a.bands != 1 || a.hits != nullptr)) return cudaErrorInvalidValue;
 
     // Candidate configurations, by shared-memory footprint (16-byte barrier slot + planes):
     //   stage 0 / 256 threads : all three planes on chip;
@@ -375,8 +473,10 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     for (const Cand &c : cands) {
         if (c.smem > budget) continue;
         const bool coop = c.stage != 0 || a.n_walls >= 128;
-        KernelChoice kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, c.stage, c.big, coop)
-                                       : pick_mode<1>(count_tests, hits, c.stage, c.big, coop);
+        KernelChoice kc;
+        if (a.n_listeners > 0) kc = count_tests ? pick_listeners<true>(c.stage, c.big, coop) : pick_listeners<false>(c.stage, c.big, coop);
+        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, c.stage, c.big, coop)
+                               : pick_mode<1>(count_tests, hits, c.stage, c.big, coop);
         cudaError_t e = cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (e != cudaSuccess) return e;
         int blocks = 0;

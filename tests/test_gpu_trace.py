@@ -232,3 +232,31 @@ def test_executed_test_count_is_a_subset_and_result_is_unchanged(ctx, oracle):
     assert e["nearest_tests"] == r["nearest_tests"] and e["nee_hits"] == r["nee_hits"] and e["direct_hits"] == r["direct_hits"]
     assert 0 < e["shadow_tests"] < r["shadow_tests"]
     assert res["prod"][1]["nearest_tests"] == 0                     # no counting without the flag
+
+
+def test_fused_listener_kernel_equals_single_listener_traces(ctx, oracle):
+    """The fused batched-listener kernel against one rar_trace per listener (which the oracle tests pin):
+    bundled room with transmission and scattering (wall_depth > 0 paths), and a 3000-wall scene
+    (warp-cooperative shadow rays), 40 listeners each."""
+    rng = np.random.default_rng(4)
+    for sc, kw, box in ((scenes.smoll_room(), None, (-19, 19, -4, 9)),
+                        (scenes.maze(n_segments=3000, ray_count=2048, max_bounces=6, bands=8), None, (5, 95, 5, 95))):
+        kw = trace_kwargs(sc, ray_count=min(sc.ray_count, 4096), impulse_length=24000)
+        listeners = np.stack([rng.uniform(box[0], box[1], 40), rng.uniform(box[2], box[3], 40)], 1).astype(np.float32)
+        ctx.set_walls(sc.walls)
+        for l in range(40):
+            ctx.ir_clear(100 + l, 24000, 1)
+            ctx.ir_clear(200 + l, 24000, 1)
+        ctx.trace_listeners(capi_params(_capi, kw), listeners, 100)
+        for l, (lx, ly) in enumerate(listeners):
+            ctx.trace(capi_params(_capi, dict(kw, listener=(float(lx), float(ly)))), 200 + l)
+        total = 0
+        for l in range(40):
+            fused, single = ctx.ir_read_fixed(100 + l, 24000), ctx.ir_read_fixed(200 + l, 24000)
+            assert np.array_equal(fused, single), l
+            total += np.count_nonzero(single)
+        assert total > 1000
+        # oracle spot check on one listener
+        lx, ly = map(float, listeners[7])
+        want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, listener=(lx, ly)))).hist
+        assert np.array_equal(ctx.ir_read_fixed(107, 24000), want)
