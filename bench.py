@@ -38,6 +38,15 @@ BOUNCES = 32
 FLOPS_PER_TEST = 20.0  # ~20 fp32 lane-ops per ray-segment test
 
 
+def _traffic(kernel: str):
+    """DRAM bytes per launch of a kernel, from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel]["bytes"]
+    except Exception:
+        return None
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -325,7 +334,7 @@ def run_ours(args):
                              "rays whose estimate cannot pass the deposit threshold; roofline.achieved uses the executed count",
             "wall_ms_per_step_incl_flush": t_wall / len(frames) * 1e3,
             "roofline": {"bound": "fp32-issue", "achieved": ach, "peak": peak, "unit": "Tlaneop/s", "frac": ach / peak,
-                         "traffic": None, "kernel": "trace_deposit_kernel",
+                         "traffic": _traffic("trace_deposit_kernel"), "kernel": "trace_deposit_kernel",
                          "note": f"{FLOPS_PER_TEST:g} fp32 lane-ops per ray-segment test (SURVEY 8d) x tests EXECUTED per launch / "
                                  "CUDA-event duration; peak = FFMA issue rate measured in this run (rar_measure_fp32_peak); "
                                  "HBM traffic is negligible for this kernel (scene 160 B, histogram 384 KB, L2 resident)"},
@@ -461,7 +470,7 @@ def bench_conv(ctx, _capi, scenes, torch, stream, dev, peaks, peaks_kind, args, 
         "e2e_samples_per_s": S * B * world / (e2e_ms * 1e-3), "e2e_ms_per_block": e2e_ms,
         "h2d_bytes_per_step": S * B * 4, "d2h_bytes_per_step": S * B * 4, "gpu_launches_per_step": 3,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                     "traffic": None, "kernel": "stream_cmac_kernel", "peak_kind": peaks_kind,
+                     "traffic": _traffic("stream_cmac_kernel"), "kernel": "stream_cmac_kernel", "peak_kind": peaks_kind,
                      "algorithmic_bytes_per_launch": bytes_per_block},
     }
 
