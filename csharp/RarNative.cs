@@ -44,6 +44,7 @@ namespace Rar2D
         public const uint FlagExactRayCount = 1u;
         public const uint FlagCountTests = 2u;
         public const uint FlagCountExecuted = 4u;
+        public const uint FlagUseGrid = 8u;
 
         [DllImport(Lib)] public static extern int rar_version();
         [DllImport(Lib)] public static extern int rar_create(int device, out IntPtr ctx);

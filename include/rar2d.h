@@ -88,6 +88,11 @@ typedef struct rar_hit_key {
  * and :227-228; ImpulseLength from RayTraceManager.cs:174.  `bands`/`time_divisor` carry the banded
  * layout of RaytraceOcclusion2D.compute:241-248 (WindowSize); ray_begin/ray_end shard one dispatch
  * across GPUs by contiguous thread-id range. */
+#define RAR_FLAG_USE_GRID 8u        /* look walls up through a uniform grid built over the scene instead of scanning
+                                       all of them.  Results are identical bit for bit; the test
+                                       counters then hold the tests actually evaluated.  Brute force is the
+                                       default and the mode the tests/s metric is quoted in. */
+
 typedef struct rar_trace_params {
     float source_pos[2];
     float listener_pos[2];

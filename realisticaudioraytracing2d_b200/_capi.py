@@ -17,6 +17,7 @@ RAR_OK = 0
 RAR_FLAG_EXACT_RAY_COUNT = 1
 RAR_FLAG_COUNT_TESTS = 2
 RAR_FLAG_COUNT_EXECUTED = 4
+RAR_FLAG_USE_GRID = 8
 
 # include/rar2d.h rar_segment / rar_ray_info / rar_hit_key
 SEGMENT_DTYPE = np.dtype(

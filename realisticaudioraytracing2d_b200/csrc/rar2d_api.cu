@@ -104,6 +104,10 @@ struct rar_context {
     int band_rows = 0, band_count = 0;
     std::vector<f4> h_geo, h_mat0;
     std::vector<f2> h_mat1;
+    std::vector<rar_segment> h_walls;  // kept for the lazy grid build
+    GridHost h_grid;
+    DevBuf<uint32_t> d_grid_start, d_grid_items;
+    bool grid_valid = false;
 
     std::vector<Slot> slots;
     DevBuf<unsigned long long> d_counters;  // 5 counters + 1 hit count
@@ -173,6 +177,41 @@ int check_trace_params(rar_context *ctx, const rar_trace_params *p) {
     if (!(p->time_divisor > 0.0f)) return fail(ctx, RAR_ERR_INVALID, "time_divisor must be positive");
     if (p->ray_begin < 0 || p->ray_end < p->ray_begin || p->ray_end > 0xffffffffLL)
         return fail(ctx, RAR_ERR_INVALID, "bad ray range");
+    return RAR_OK;
+}
+
+// Builds (once per wall upload) and attaches the uniform grid when the call asks for it.
+int attach_grid(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
+    a.use_grid = 0;
+    if (!(p->flags & RAR_FLAG_USE_GRID) || ctx->n_walls <= 0) return RAR_OK;
+    if (!ctx->grid_valid) {
+        build_grid(ctx->h_walls.data(), ctx->n_walls, ctx->h_grid);
+        const GridHost &g = ctx->h_grid;
+        if (g.nx > 0) {
+            RAR_CUDA(ctx, ctx->d_grid_start.reserve(g.cell_start.size()));
+            RAR_CUDA(ctx, ctx->d_grid_items.reserve(g.items.size() + 1));
+            RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_start.p, g.cell_start.data(), g.cell_start.size() * sizeof(uint32_t),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+            if (!g.items.empty())
+                RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_items.p, g.items.data(), g.items.size() * sizeof(uint32_t),
+                                              cudaMemcpyHostToDevice, ctx->stream));
+            RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->grid_valid = true;
+    }
+    const GridHost &g = ctx->h_grid;
+    if (g.nx <= 0) return RAR_OK;  // no grid could be built (non-finite coordinates): brute force
+    a.grid.x0 = g.x0;
+    a.grid.y0 = g.y0;
+    a.grid.cw = g.cw;
+    a.grid.ch = g.ch;
+    a.grid.inv_cw = 1.0f / g.cw;
+    a.grid.inv_ch = 1.0f / g.ch;
+    a.grid.nx = g.nx;
+    a.grid.ny = g.ny;
+    a.grid.cell_start = ctx->d_grid_start.p;
+    a.grid.items = ctx->d_grid_items.p;
+    a.use_grid = 1;
     return RAR_OK;
 }
 
@@ -299,6 +338,8 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_irf.release();
     ctx->d_listeners.release();
     ctx->d_listener_hists.release();
+    ctx->d_grid_start.release();
+    ctx->d_grid_items.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RAR_OK;
@@ -344,6 +385,8 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
         ctx->band_count = 0;
     }
     ctx->n_walls = n;
+    ctx->h_walls.assign(segments, segments + n);
+    ctx->grid_valid = false;
     return RAR_OK;
 }
 
@@ -457,6 +500,8 @@ int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) {
         return fail(ctx, RAR_ERR_INVALID, "params impulse_length/bands do not match the slot");
     TraceLaunch a;
     fill_launch(ctx, params, a);
+    rc = attach_grid(ctx, params, a);
+    if (rc != RAR_OK) return rc;
     a.hist = reinterpret_cast<unsigned long long *>(S->d_hist);
     const bool count = (params->flags & RAR_FLAG_COUNT_TESTS) != 0;
     a.counters = count ? ctx->d_counters.p : nullptr;
@@ -517,6 +562,8 @@ int rar_trace_listeners(rar_context *ctx, const rar_trace_params *params, const 
     RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors are pageable
     TraceLaunch a;
     fill_launch(ctx, params, a);
+    rc = attach_grid(ctx, params, a);
+    if (rc != RAR_OK) return rc;
     a.listeners = ctx->d_listeners.p;
     a.listener_hists = ctx->d_listener_hists.p;
     a.n_listeners = n_listeners;

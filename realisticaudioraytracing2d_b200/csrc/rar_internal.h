@@ -33,6 +33,9 @@ struct TraceLaunch {
     const f2 *listeners;
     unsigned long long *const *listener_hists;
     int n_listeners;
+    // optional uniform grid (RAR_FLAG_USE_GRID); use_grid selects the grid instantiation
+    GridView grid;
+    int use_grid;
 };
 
 struct DeviceFacts {

@@ -8,6 +8,10 @@
 // the same binary32 subtraction, so results are unchanged.
 #pragma once
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "../../include/rar2d.h"
 #include "rar_ray.cuh"
 
@@ -41,6 +45,71 @@ inline RayConsts ray_consts(const rar_trace_params &p) {
     c.time_divisor = p.time_divisor;
     c.count_executed = (p.flags & RAR_FLAG_COUNT_EXECUTED) ? 1 : 0;
     return c;
+}
+
+// Uniform grid over the walls for RAR_FLAG_USE_GRID (see rar_ray.cuh GridView).  Conservative by construction:
+// a wall is registered in every cell whose box, grown by the margin m, meets the wall's supporting strip
+// (separating-axis test on the wall's normal, inside the wall's bounding box grown by m).
+struct GridHost {
+    float x0 = 0, y0 = 0, cw = 1, ch = 1;
+    int nx = 0, ny = 0;
+    std::vector<uint32_t> cell_start, items;
+};
+
+inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
+    g = GridHost();
+    if (n <= 0) return;
+    double minx = 1e300, miny = 1e300, maxx = -1e300, maxy = -1e300, maxabs = 0;
+    for (int w = 0; w < n; w++) {
+        for (int e = 0; e < 2; e++) {
+            const double x = e ? walls[w].end[0] : walls[w].start[0], y = e ? walls[w].end[1] : walls[w].start[1];
+            if (!(std::isfinite(x) && std::isfinite(y))) return;  // no grid for non-finite scenes: brute force handles them
+            minx = std::min(minx, x); maxx = std::max(maxx, x);
+            miny = std::min(miny, y); maxy = std::max(maxy, y);
+            maxabs = std::max(maxabs, std::max(std::fabs(x), std::fabs(y)));
+        }
+    }
+    const double pad = 1e-3 * std::max(maxx - minx, maxy - miny) + 1e-4;
+    minx -= pad; miny -= pad; maxx += pad; maxy += pad;
+    const double ex = maxx - minx, ey = maxy - miny;
+    const double target_cells = std::max(1.0, n / 2.0);
+    const double cell = std::sqrt(ex * ey / target_cells);
+    const int nx = (int)std::min(2048.0, std::max(1.0, std::ceil(ex / cell)));
+    const int ny = (int)std::min(2048.0, std::max(1.0, std::ceil(ey / cell)));
+    const double cw = ex / nx, ch = ey / ny;
+    const double ulp = std::ldexp(std::max(maxabs, 1e-30), -23);
+    const double m = std::max(0.02 * std::min(cw, ch), 128.0 * ulp);
+    g.x0 = (float)minx; g.y0 = (float)miny; g.cw = (float)cw; g.ch = (float)ch; g.nx = nx; g.ny = ny;
+    // use the float-rounded frame the device will use
+    const double fx0 = g.x0, fy0 = g.y0, fcw = g.cw, fch = g.ch;
+    std::vector<uint32_t> count((size_t)nx * ny + 1, 0);
+    for (int pass = 0; pass < 2; pass++) {
+        for (int w = 0; w < n; w++) {
+            const double ax = walls[w].start[0], ay = walls[w].start[1], bx = walls[w].end[0], by = walls[w].end[1];
+            const double vx = bx - ax, vy = by - ay;
+            int ix0 = (int)std::floor((std::min(ax, bx) - m - fx0) / fcw), ix1 = (int)std::floor((std::max(ax, bx) + m - fx0) / fcw);
+            int iy0 = (int)std::floor((std::min(ay, by) - m - fy0) / fch), iy1 = (int)std::floor((std::max(ay, by) + m - fy0) / fch);
+            ix0 = std::max(ix0, 0); iy0 = std::max(iy0, 0); ix1 = std::min(ix1, nx - 1); iy1 = std::min(iy1, ny - 1);
+            const double hx = 0.5 * fcw + m, hy = 0.5 * fch + m;
+            const double reach = std::fabs(vy) * hx + std::fabs(vx) * hy;
+            for (int iy = iy0; iy <= iy1; iy++) {
+                for (int ix = ix0; ix <= ix1; ix++) {
+                    const double cx = fx0 + (ix + 0.5) * fcw, cy = fy0 + (iy + 0.5) * fch;
+                    const double dist = std::fabs(vx * (cy - ay) - vy * (cx - ax));
+                    if (dist > reach * (1.0 + 1e-9) + 1e-300) continue;
+                    const size_t cell_id = (size_t)iy * nx + ix;
+                    if (pass == 0) count[cell_id + 1]++;
+                    else g.items[g.cell_start[cell_id] + count[cell_id]++] = (uint32_t)w;
+                }
+            }
+        }
+        if (pass == 0) {
+            g.cell_start.assign((size_t)nx * ny + 1, 0);
+            for (size_t c = 0; c < (size_t)nx * ny; c++) g.cell_start[c + 1] = g.cell_start[c] + count[c + 1];
+            g.items.assign(g.cell_start.back(), 0);
+            std::fill(count.begin(), count.end(), 0);
+        }
+    }
 }
 
 // Thread-id range a trace call covers: the reference dispatches ceil(rayCount/64) groups of 64 threads

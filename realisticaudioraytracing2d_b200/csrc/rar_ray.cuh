@@ -113,11 +113,155 @@ RAR_HD bool wall_pass(const WallTest &t, float bound_m) {
     return (fabsf(rar_fma(2.0f, t.num2, -t.dotP)) <= fabsf(t.dotP)) & (fabsf(rar_fma(2.0f, t.num1, -r)) <= fabsf(r));
 }
 
+// ---- optional uniform grid over the walls (RAR_FLAG_USE_GRID) -------------------------------------------
+//
+// SURVEY.md 8(f)-2.  Brute force stays the default and the measured mode; the grid changes which walls are
+// LOOKED AT, never the outcome: every wall a query could accept is still evaluated with the same filter and
+// the same literal formula, and ties are broken by wall index exactly as the ascending brute-force scan does.
+// Why nothing is missed: a wall is registered in every cell within a margin m of any of its points
+// (m = 2 % of a cell, at least 128 ulp of the largest coordinate; rar_layout.h build_grid), and the cell walk
+// follows the ray to within float rounding (<< m).  So a point of the ray that is farther than m from every
+// visited cell does not exist, and a wall whose hit point lies on the visited stretch of the ray is registered
+// in a visited cell.  The nearest-hit walk stops once the best hit lies before the exit of the current cell.
+struct GridView {
+    float x0, y0;          // lower corner of cell (0, 0)
+    float cw, ch;          // cell size
+    float inv_cw, inv_ch;
+    int nx, ny;
+    const uint32_t *cell_start;  // [nx * ny + 1]
+    const uint32_t *items;       // wall indices, ascending within a cell
+};
+
+struct GridWalk {
+    int ix, iy, stepx, stepy;
+    float tmx, tmy, tdx, tdy;  // ray parameter of the next x / y cell boundary, and per-cell increments
+};
+
+// Clips the half-line o + t d, t >= 0, to the grid and positions the walk on its first cell.
+RAR_HD bool grid_walk_init(const GridView &g, float ox, float oy, float dx, float dy, GridWalk &w) {
+    const float bx1 = g.x0 + (float)g.nx * g.cw, by1 = g.y0 + (float)g.ny * g.ch;
+    const float big = 3.0e38f;
+    float t0 = 0.0f, t1 = big;
+    const float idx = dx != 0.0f ? 1.0f / dx : 0.0f, idy = dy != 0.0f ? 1.0f / dy : 0.0f;
+    if (dx != 0.0f) {
+        const float ta = (g.x0 - ox) * idx, tb = (bx1 - ox) * idx;
+        t0 = fmaxf(t0, fminf(ta, tb));
+        t1 = fminf(t1, fmaxf(ta, tb));
+    } else if (ox < g.x0 || ox > bx1) {
+        return false;
+    }
+    if (dy != 0.0f) {
+        const float ta = (g.y0 - oy) * idy, tb = (by1 - oy) * idy;
+        t0 = fmaxf(t0, fminf(ta, tb));
+        t1 = fminf(t1, fmaxf(ta, tb));
+    } else if (oy < g.y0 || oy > by1) {
+        return false;
+    }
+    if (!(t0 <= t1)) return false;
+    const float px = ox + dx * t0, py = oy + dy * t0;
+    int ix = (int)floorf((px - g.x0) * g.inv_cw), iy = (int)floorf((py - g.y0) * g.inv_ch);
+    ix = ix < 0 ? 0 : (ix >= g.nx ? g.nx - 1 : ix);
+    iy = iy < 0 ? 0 : (iy >= g.ny ? g.ny - 1 : iy);
+    w.ix = ix;
+    w.iy = iy;
+    w.stepx = dx > 0.0f ? 1 : -1;
+    w.stepy = dy > 0.0f ? 1 : -1;
+    w.tmx = dx != 0.0f ? (g.x0 + (float)(ix + (dx > 0.0f ? 1 : 0)) * g.cw - ox) * idx : big;
+    w.tmy = dy != 0.0f ? (g.y0 + (float)(iy + (dy > 0.0f ? 1 : 0)) * g.ch - oy) * idy : big;
+    w.tdx = dx != 0.0f ? g.cw * fabsf(idx) : big;
+    w.tdy = dy != 0.0f ? g.ch * fabsf(idy) : big;
+    return true;
+}
+
+// Moves to the next cell along the ray; false when the walk leaves the grid.
+RAR_HD bool grid_walk_step(const GridView &g, GridWalk &w) {
+    if (w.tmx < w.tmy) {
+        w.ix += w.stepx;
+        w.tmx += w.tdx;
+        return w.ix >= 0 && w.ix < g.nx;
+    }
+    w.iy += w.stepy;
+    w.tmy += w.tdy;
+    return w.iy >= 0 && w.iy < g.ny;
+}
+
+template <class Scene>
+RAR_HD void nearest_hit_grid(const Scene &sc, float ox, float oy, float dx, float dy, float &closest_out, int &hit_out,
+                             int *tests) {
+    float closest = kInf, closest_m = kInf * kSlack;
+    int hit = -1, n_tests = 0;
+    const float ndy = -dy;
+    const GridView &g = sc.grid();
+    GridWalk w;
+    if (g.nx > 0 && grid_walk_init(g, ox, oy, dx, dy, w)) {
+        for (int guard = g.nx + g.ny + 2; guard > 0; guard--) {
+            const int cell = w.iy * g.nx + w.ix;
+            const uint32_t i0 = g.cell_start[cell], i1 = g.cell_start[cell + 1];
+            for (uint32_t i = i0; i < i1; i++) {
+                const int k = (int)g.items[i];
+                const WallTest t = wall_test(sc.geo(k), ox, oy, dx, ndy);
+                n_tests++;
+                if (wall_pass(t, closest_m)) {
+                    const float d = intersect_exact(t.num1, t.num2, t.dotP);
+                    // cells are not visited in wall order: break ties by index like the ascending scan does
+                    if (d < closest || (d == closest && d < kInf && k < hit)) {
+                        closest = d;
+                        closest_m = d * kSlack;
+                        hit = k;
+                    }
+                }
+            }
+            if (closest <= fminf(w.tmx, w.tmy)) break;  // the best hit lies before this cell's exit
+            if (!grid_walk_step(g, w)) break;
+        }
+    }
+    if (tests) *tests = n_tests;
+    closest_out = closest;
+    hit_out = hit;
+}
+
+template <class Scene>
+RAR_HD bool check_vis_grid(const Scene &sc, float sx, float sy, float dx, float ndy, float lim, int *tests) {
+    const GridView &g = sc.grid();
+    int n_tests = 0;
+    bool blocked = false;
+    if (sc.n_walls() > 0 && kInf < lim) {
+        blocked = true;  // every intersect() result (<= inf) is < lim
+        n_tests = 1;
+    } else {
+        const float lim_m = lim * kSlack;
+        GridWalk w;
+        if (g.nx > 0 && grid_walk_init(g, sx, sy, dx, -ndy, w)) {
+            for (int guard = g.nx + g.ny + 2; guard > 0 && !blocked; guard--) {
+                const int cell = w.iy * g.nx + w.ix;
+                const uint32_t i0 = g.cell_start[cell], i1 = g.cell_start[cell + 1];
+                for (uint32_t i = i0; i < i1; i++) {
+                    const WallTest t = wall_test(sc.geo((int)g.items[i]), sx, sy, dx, ndy);
+                    n_tests++;
+                    if (wall_pass(t, lim_m) && intersect_exact(t.num1, t.num2, t.dotP) < lim) {
+                        blocked = true;
+                        break;
+                    }
+                }
+                if (fminf(w.tmx, w.tmy) >= lim) break;  // walls beyond the limit cannot block
+                if (!grid_walk_step(g, w)) break;
+            }
+        }
+    }
+    if (tests) *tests = n_tests;
+    return !blocked;
+}
+
 // Raytrace2D.compute:69-72: nearest hit over all walls, lowest index wins ties.  Walls are filtered four
 // at a time against the same bound so that the common case is four independent loads, four filters and
 // a single branch; survivors are then evaluated literally, in wall order.
 template <class Scene>
-RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy, float &closest_out, int &hit_out) {
+RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy, float &closest_out, int &hit_out,
+                        int *grid_tests = nullptr) {
+    if constexpr (Scene::kGrid) {
+        nearest_hit_grid(sc, ox, oy, dx, dy, closest_out, hit_out, grid_tests);
+        return;
+    }
     float closest = kInf, closest_m = kInf * kSlack;
     int hit = -1;
     const float ndy = -dy;
@@ -185,6 +329,7 @@ RAR_HD bool shadow_blocked_by(const f4 s, const ShadowRay &q, float lim_m) {
 // the number of intersect() evaluations the reference's loop performs (first blocking wall + 1, else n).
 template <class Scene>
 RAR_HD bool check_vis(const Scene &sc, const ShadowRay &q, int *tests) {
+    if constexpr (Scene::kGrid) return check_vis_grid(sc, q.sx, q.sy, q.dx, q.ndy, q.lim, tests);
     const int n = sc.n_walls();
     if (n > 0 && kInf < q.lim) {  // every intersect() result (<= inf) is < lim: blocked by wall 0
         if (tests) *tests = 1;
@@ -251,10 +396,11 @@ struct BounceCtx {
 // :69-72
 template <int BANDS, bool COUNT, class Scene>
 RAR_HD void bounce_nearest(const Scene &sc, const RayState<BANDS> &r, BounceCtx<BANDS> &c, RayCounters *ctr) {
-    nearest_hit(sc, r.px, r.py, r.dx, r.dy, c.closest, c.hit);
+    int tests = sc.n_walls();  // brute force: the reference's count; grid: the tests actually evaluated
+    nearest_hit(sc, r.px, r.py, r.dx, r.dy, c.closest, c.hit, (COUNT && Scene::kGrid) ? &tests : nullptr);
     if (COUNT) {
         ctr->ray_bounces += 1;
-        ctr->nearest_tests += (unsigned long long)sc.n_walls();
+        ctr->nearest_tests += (unsigned long long)tests;
     }
 }
 

@@ -62,13 +62,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 
 // STAGE 0: endpoint and material planes in shared memory; 1: endpoints in shared, materials in global;
 // 2: everything read through the read-only global path (scenes too large for shared memory).
-template <int STAGE>
+template <int STAGE, bool GRID = false>
 struct SceneView {
+    static constexpr bool kGrid = GRID;
     const f4 *g;
     const f4 *m0;
     const f2 *m1;
     const float *ba;
     int n, nb;
+    GridView gv;
+    __device__ __forceinline__ const GridView &grid() const { return gv; }
     __device__ __forceinline__ int n_walls() const { return n; }
     __device__ __forceinline__ f4 geo(int w) const {
         if (STAGE == 2) {
@@ -197,8 +200,8 @@ __device__ __forceinline__ bool coop_shadow(const Scene &sc, bool pending, const
 
 // Stages the wall planes into shared memory with 1-D TMA bulk copies (STAGE 0: all three planes, STAGE 1: the
 // endpoint plane) and returns the view the ray code reads.  All threads of the CTA call this once.
-template <int STAGE>
-__device__ __forceinline__ SceneView<STAGE> stage_scene(const TraceLaunch &a, unsigned char *smem_raw) {
+template <int STAGE, bool GRID>
+__device__ __forceinline__ SceneView<STAGE, GRID> stage_scene(const TraceLaunch &a, unsigned char *smem_raw) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     f4 *s_geo = reinterpret_cast<f4 *>(smem_raw + 16);
     f4 *s_mat0 = s_geo + a.n_walls;
@@ -225,7 +228,8 @@ __device__ __forceinline__ SceneView<STAGE> stage_scene(const TraceLaunch &a, un
         }
     }
 
-    SceneView<STAGE> sc;
+    SceneView<STAGE, GRID> sc;
+    sc.gv = a.grid;
     sc.g = STAGE < 2 ? s_geo : a.geo;
     sc.m0 = STAGE == 0 ? s_mat0 : a.mat0;
     sc.m1 = STAGE == 0 ? s_mat1 : a.mat1;
@@ -237,10 +241,10 @@ __device__ __forceinline__ SceneView<STAGE> stage_scene(const TraceLaunch &a, un
 
 // ---- the kernel -------------------------------------------------------------------------------------
 
-template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP>
+template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false>
 __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SceneView<STAGE> sc = stage_scene<STAGE>(a, smem_raw);
+    const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
 
     const unsigned lane = threadIdx.x & 31u;
     const long long n_rays = a.ray_end - a.ray_begin;
@@ -317,11 +321,11 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
 // nearest-hit loop once and then, for every listener, only the listener pieces: the direct crossing test
 // before the advance, and the next-event estimate with its shadow ray after it.  Listener l deposits into its
 // own histogram.  Result per listener: identical to a single-listener trace (same pieces, same order).
-template <bool COUNT, int STAGE, int MAXT, bool COOP>
+template <bool COUNT, int STAGE, int MAXT, bool COOP, bool GRID = false>
 __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_constant__ TraceLaunch a) {
     constexpr int BANDS = 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SceneView<STAGE> sc = stage_scene<STAGE>(a, smem_raw);
+    const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
 
     const unsigned lane = threadIdx.x & 31u;
     const long long n_rays = a.ray_end - a.ray_begin;
@@ -470,7 +474,25 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     size_t smem = 0;
     bool big_block = false;
     int best_resident = -1, per_sm = 0;
+    if (a.use_grid) {
+        // Grid walks touch a few walls per query at data-dependent addresses: no staging, per-thread shadow walk.
+        if (a.hits != nullptr) return cudaErrorInvalidValue;
+        if (a.n_listeners > 0)
+            k = count_tests ? KernelChoice{(const void *)trace_listeners_kernel<true, 2, 256, false, true>, 256}
+                            : KernelChoice{(const void *)trace_listeners_kernel<false, 2, 256, false, true>, 256};
+        else if (a.bands == 8)
+            k = count_tests ? KernelChoice{(const void *)trace_deposit_kernel<8, true, false, 2, 256, false, true>, 256}
+                            : KernelChoice{(const void *)trace_deposit_kernel<8, false, false, 2, 256, false, true>, 256};
+        else
+            k = count_tests ? KernelChoice{(const void *)trace_deposit_kernel<1, true, false, 2, 256, false, true>, 256}
+                            : KernelChoice{(const void *)trace_deposit_kernel<1, false, false, 2, 256, false, true>, 256};
+        smem = 16;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.max_threads, smem);
+        if (e != cudaSuccess) return e;
+        best_resident = per_sm * k.max_threads;
+    }
     for (const Cand &c : cands) {
+        if (a.use_grid) break;
         if (c.smem > budget) continue;
         const bool coop = c.stage != 0 || a.n_walls >= 128;
         KernelChoice kc;

@@ -9,7 +9,11 @@
 #include "../realisticaudioraytracing2d_b200/csrc/rar_layout.h"
 
 namespace {
-struct HostScene {
+template <bool GRID>
+struct HostSceneT {
+    static constexpr bool kGrid = GRID;
+    rar::GridView gv;
+    const rar::GridView &grid() const { return gv; }
     const rar::f4 *g, *m0;
     const rar::f2 *m1;
     const float *ba;
@@ -20,11 +24,12 @@ struct HostScene {
     rar::f2 mat1(int w) const { return m1[w]; }
     const float *band_abs(int w) const { return ba + (size_t)w * nb; }
 };
+using HostScene = HostSceneT<false>;
 
 struct Hit { float t, e, x, y; uint32_t ray; uint16_t bounce, kind; };
 
-template <int BANDS, bool COUNT>
-void run(const HostScene &sc, const rar_trace_params &p, long long *hist, Hit *hits, long long cap, long long *count,
+template <int BANDS, bool COUNT, class SceneT>
+void run(const SceneT &sc, const rar_trace_params &p, long long *hist, Hit *hits, long long cap, long long *count,
          rar::RayCounters &ctr) {
     rar::RayConsts c = rar::ray_consts(p);
     long long lo, hi;
@@ -59,10 +64,25 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
     std::vector<rar::f4> g(n + 1), m0(n + 1);
     std::vector<rar::f2> m1(n + 1);
     rar::split_walls(walls, n, g.data(), m0.data(), m1.data());
-    HostScene sc{g.data(), m0.data(), m1.data(), band_abs, n, p->bands};
     rar::RayCounters ctr;
     std::memset(&ctr, 0, sizeof ctr);
     long long cnt = 0;
+    if (p->flags & RAR_FLAG_USE_GRID) {  // the uniform-grid instantiation (broadband only in this harness)
+        rar::GridHost gh;
+        rar::build_grid(walls, n, gh);
+        if (gh.nx <= 0 || p->bands > 1) return -6;
+        HostSceneT<true> sg;
+        sg.gv = rar::GridView{gh.x0, gh.y0, gh.cw, gh.ch, 1.0f / gh.cw, 1.0f / gh.ch, gh.nx, gh.ny, gh.cell_start.data(), gh.items.data()};
+        sg.g = g.data(); sg.m0 = m0.data(); sg.m1 = m1.data(); sg.ba = band_abs; sg.n = n; sg.nb = p->bands;
+        if (counting) run<1, true>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else run<1, false>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        if (count) *count = cnt;
+        if (out) { out->ray_bounces = ctr.ray_bounces; out->nearest_tests = ctr.nearest_tests; out->shadow_tests = ctr.shadow_tests;
+                   out->direct_hits = ctr.direct_hits; out->nee_hits = ctr.nee_hits; }
+        return 0;
+    }
+    HostScene sc;
+    sc.g = g.data(); sc.m0 = m0.data(); sc.m1 = m1.data(); sc.ba = band_abs; sc.n = n; sc.nb = p->bands;
     if (p->bands <= 1) {
         if (counting) run<1, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
         else run<1, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);

@@ -260,3 +260,55 @@ def test_fused_listener_kernel_equals_single_listener_traces(ctx, oracle):
         lx, ly = map(float, listeners[7])
         want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, listener=(lx, ly)))).hist
         assert np.array_equal(ctx.ir_read_fixed(107, 24000), want)
+
+
+@pytest.mark.parametrize("bands", [1, 8])
+def test_grid_mode_is_bit_identical_to_brute_force(ctx, oracle, bands):
+    """RAR_FLAG_USE_GRID changes which walls are looked at, never the result: same histogram as the brute-force
+    kernel and as the oracle, for the broadband and the banded kernel."""
+    sc = scenes.maze(n_segments=10000, ray_count=30_000, max_bounces=24, bands=8)
+    kw = trace_kwargs(sc, bands=bands)
+    n = kw["impulse_length"] * bands
+    ctx.set_walls(sc.walls)
+    ctx.set_wall_band_absorption(sc.band_absorption)
+    ctx.ir_clear(0, kw["impulse_length"], bands)
+    ctx.trace(capi_params(_capi, kw), 0)
+    brute = ctx.ir_read_fixed(0, n)
+    ctx.ir_clear(1, kw["impulse_length"], bands)
+    ctx.get_counters(reset=True)
+    ctx.trace(capi_params(_capi, dict(kw, flags=_capi.RAR_FLAG_USE_GRID | _capi.RAR_FLAG_COUNT_TESTS)), 1)
+    grid = ctx.ir_read_fixed(1, n)
+    c = ctx.get_counters()
+    assert np.array_equal(grid, brute) and np.count_nonzero(brute) > 100
+    assert 0 < c["nearest_tests"] < c["ray_bounces"] * 200          # a few walls per query instead of 10 000
+    want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw), band_abs=sc.band_absorption if bands > 1 else None).hist
+    assert np.array_equal(grid, want)
+
+
+def test_grid_mode_bundled_room_listeners_and_geometry_update(ctx, oracle):
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc, flags=_capi.RAR_FLAG_USE_GRID)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace(capi_params(_capi, kw), 0)
+    want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, trace_kwargs(sc))).hist
+    assert np.array_equal(ctx.ir_read_fixed(0, n), want)
+    # new geometry invalidates the cached grid
+    sc2 = scenes.big_room()
+    ctx.set_walls(sc2.walls)
+    kw2 = trace_kwargs(sc2, flags=_capi.RAR_FLAG_USE_GRID)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace(capi_params(_capi, kw2), 0)
+    want = oracle.trace(oracle_walls(oracle, sc2.walls), oracle_params(oracle, trace_kwargs(sc2))).hist
+    assert np.array_equal(ctx.ir_read_fixed(0, n), want)
+    # fused listeners through the grid
+    rng = np.random.default_rng(3)
+    listeners = np.stack([rng.uniform(-150, 150, 12), rng.uniform(-40, 80, 12)], 1).astype(np.float32)
+    for l in range(12):
+        ctx.ir_clear(20 + l, n, 1)
+    ctx.trace_listeners(capi_params(_capi, kw2), listeners, 20)
+    for l in (0, 5, 11):
+        lx, ly = map(float, listeners[l])
+        want = oracle.trace(oracle_walls(oracle, sc2.walls), oracle_params(oracle, dict(trace_kwargs(sc2), listener=(lx, ly)))).hist
+        assert np.array_equal(ctx.ir_read_fixed(20 + l, n), want), l

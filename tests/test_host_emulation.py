@@ -123,3 +123,67 @@ def test_filtered_intersection_equals_literal_formula(oracle):
     want = np.where(want < closest, want, np.float32(1e8))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert (want < 1e8).sum() > n // 20
+
+
+# ---- uniform-grid mode (RAR_FLAG_USE_GRID): identical results to the brute-force oracle ------------------------
+
+def _check_grid(O, sc, kw):
+    P = oracle_params(O, dict(kw, flags=kw["flags"] | 8))
+    r = O.trace(oracle_walls(O, sc.walls), oracle_params(O, kw), want_hits=True)
+    for counting in (True, False):
+        hist, hits, _ = emulation.trace(O, sc.walls, P, None, counting=counting)
+        assert np.array_equal(hist, r.hist)
+        assert len(hits) == len(r.hits) and hits.tobytes() == r.hits.tobytes()
+    return r
+
+
+@pytest.mark.parametrize("frame", [1, 5])
+def test_grid_mode_bundled_rooms(oracle, frame):
+    for sc in (scenes.smoll_room(), scenes.big_room()):      # long rotated walls spanning many cells
+        _check_grid(oracle, sc, trace_kwargs(sc, ray_count=4000, rng_state_offset=frame, max_bounce_count=8))
+
+
+@pytest.mark.parametrize("n_segments,seed", [(300, 1), (2000, 2), (6000, 3)])
+def test_grid_mode_mazes(oracle, n_segments, seed):
+    sc = scenes.maze(n_segments=n_segments, ray_count=3000, max_bounces=20, bands=8, seed=seed)
+    r = _check_grid(oracle, sc, trace_kwargs(sc))
+    assert r.n_hits > 50
+
+
+def test_grid_mode_shoebox_and_axis_aligned_rays(oracle):
+    sc = scenes.shoebox(ray_count=20000, max_bounces=32, scattering=0.2, transmission=0.3, ior=1.2)
+    _check_grid(oracle, sc, trace_kwargs(sc))
+    sc = scenes.shoebox(ray_count=4, max_bounces=16)
+    sc.source = (5.0, 3.0)                                   # rays along cell boundaries of the grid
+    for frame in range(1, 20):
+        _check_grid(oracle, sc, trace_kwargs(sc, ray_count=4, rng_state_offset=frame, flags=1))
+
+
+def test_grid_mode_rays_leaving_an_open_scene(oracle):
+    sc = scenes.smoll_room()
+    sc.walls = sc.walls[[0, 1, 2, 3, 16, 17]]                # open on several sides: rays escape the grid
+    _check_grid(oracle, sc, trace_kwargs(sc, ray_count=5000))
+    sc.source = (-80.0, 30.0)                                # source outside the walls' bounding box
+    _check_grid(oracle, sc, trace_kwargs(sc, ray_count=5000))
+
+
+def test_grid_mode_random_soup_of_segments(oracle):
+    """Random overlapping, crossing, tiny and long segments with shared endpoints: nothing grid-friendly."""
+    from realisticaudioraytracing2d_b200.host.scene_helper import SEGMENT_DTYPE
+    rng = np.random.default_rng(9)
+    n = 1500
+    a = rng.uniform(0, 50, (n, 2)).astype(np.float32)
+    length = np.where(rng.random(n) < 0.1, rng.uniform(5, 40, n), rng.uniform(0.01, 2.0, n))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    b = (a + np.stack([np.cos(ang), np.sin(ang)], 1) * length[:, None]).astype(np.float32)
+    b[1::7] = a[0:-1:7][: len(b[1::7])]                      # shared endpoints
+    walls = np.zeros(n, dtype=SEGMENT_DTYPE)
+    walls["start"], walls["end"] = a, b
+    d = b - a
+    nrm = np.stack([d[:, 1], -d[:, 0]], 1) / np.maximum(np.hypot(d[:, 0], d[:, 1]), 1e-9)[:, None]
+    walls["normal"] = nrm.astype(np.float32)
+    walls["absorption"], walls["scattering"], walls["transmission"], walls["ior"] = 0.1, 0.3, 0.2, 1.1
+    sc = scenes.smoll_room()
+    sc.walls, sc.source, sc.listener = walls, (25.0, 25.0), (30.0, 22.0)
+    r = _check_grid(oracle, sc, trace_kwargs(sc, ray_count=4000, max_bounce_count=12))
+    assert r.counters["ray_bounces"] > 20000

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--walls", type=int, default=10000)
     ap.add_argument("--bands", type=int, default=8)
     ap.add_argument("--count", action="store_true")
+    ap.add_argument("--grid", action="store_true", help="RAR_FLAG_USE_GRID: same histogram, far fewer tests")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -49,7 +50,10 @@ def main():
     hist = sharding.DeviceHistogram(ctx, 0, dev).tensor
     lo, hi = sharding.shard_range(sharding.dispatched_threads(a.rays), rank, world)
 
+    base_flags = _capi.RAR_FLAG_USE_GRID if a.grid else 0
+
     def prm(flags=0):
+        flags |= base_flags
         return _capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
                                        a.bounces, 1, a.rays, 0, sc.sample_rate, n, a.bands, 1.0, flags, lo, hi)
     # warm-up on a sliver of the range
@@ -84,7 +88,7 @@ def main():
         tests = float(t[0])
     if rank == 0:
         print(json.dumps({"config": f"config3: {a.walls}-wall maze, {a.rays} rays x {a.bounces} bounces, {a.bands} bands, 48000 bins",
-                          "n_gpus": world, "scaling": "strong", "ir_build_ms": float(ms[0]), "tests": tests,
+                          "n_gpus": world, "scaling": "strong", "grid": bool(a.grid), "ir_build_ms": float(ms[0]), "tests": tests,
                           "tests_per_s": tests / (float(ms[0]) * 1e-3) if tests else None,
                           "histogram_sha256": digest, "nonzero_words": nz}), flush=True)
     if world > 1:

@@ -43,6 +43,8 @@ def main():
         ctx.set_wall_band_absorption(sc.band_absorption)
     p = _capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain, sc.max_bounces,
                                 1, sc.ray_count, 100 if what == "c2" else 0, sc.sample_rate, n, bands)
+    if os.environ.get("RAR_GRID"):
+        p.flags = _capi.RAR_FLAG_USE_GRID
     for r in range(reps):
         ctx.ir_clear(0, n, bands)
         ctx.sync()
@@ -51,7 +53,7 @@ def main():
         ctx.sync()
         print(f"{what} trace {1e3 * (time.perf_counter() - t0):.3f} ms")
     ctx.get_counters(reset=True)
-    p.flags = _capi.RAR_FLAG_COUNT_TESTS
+    p.flags |= _capi.RAR_FLAG_COUNT_TESTS
     ctx.ir_clear(0, n, bands)
     ctx.trace(p, 0)
     c = ctx.get_counters()
