@@ -382,6 +382,20 @@ def bench_maze(ctx, _capi, scenes, torch, stream, flush):
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         out[f"bands{bands}"] = {"tests": tests, "ms": best, "tests_per_s": tests / (best * 1e-3)}
+        # the same IR through the optional uniform grid (identical histogram, far fewer tests evaluated)
+        ref = ctx.ir_read_fixed(2, n * bands)
+        gbest = 1e30
+        for _ in range(3):
+            flush.zero_()
+            ctx.ir_clear(2, n, bands)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.trace(prm(_capi.RAR_FLAG_USE_GRID), 2)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            gbest = min(gbest, e0.elapsed_time(e1))
+        out[f"bands{bands}"]["grid_ms"] = gbest
+        out[f"bands{bands}"]["grid_identical"] = bool(np.array_equal(ctx.ir_read_fixed(2, n * bands), ref))
     out["workload"] = f"config3 geometry: 10000-wall maze, {sc.ray_count} rays x 16 bounces (reduced ray count)"
     return out
 
