@@ -18,6 +18,7 @@ using Rar2D;
 public class RayTraceManager : MonoBehaviour
 {
     [Header("Native")] public int cudaDevice = 0;
+    public int gridThreshold = 64;   // wall count from which traces use the uniform grid (identical results)
 
     [Header("Simulation")]
     [Range(10, 100000)] public int rayCount = 1000;
@@ -152,7 +153,7 @@ public class RayTraceManager : MonoBehaviour
             listenerRadius = listenerRadius, speedOfSound = speedOfSound, inputGain = inputGain,
             maxBounceCount = maxBounces, rngStateOffset = (uint)Time.frameCount, rayCount = rayCount,
             debugRayCount = debugRayCount, sampleRate = sampleRate, impulseLength = IrLength,
-            bands = 1, timeDivisor = 1f, flags = 0, rayBegin = 0, rayEnd = 0,
+            bands = 1, timeDivisor = 1f, flags = walls.Length >= gridThreshold ? RarNative.FlagUseGrid : 0u, rayBegin = 0, rayEnd = 0,
         };
         if (RarNative.Ok(native, RarNative.rar_trace(native, ref p, ActiveSlot()), "trace")) accumFrames++;
     }

@@ -107,6 +107,7 @@ struct rar_context {
     std::vector<rar_segment> h_walls;  // kept for the lazy grid build
     GridHost h_grid;
     DevBuf<uint32_t> d_grid_start, d_grid_items;
+    DevBuf<f4> d_grid_geo;
     bool grid_valid = false;
 
     std::vector<Slot> slots;
@@ -192,9 +193,13 @@ int attach_grid(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
             RAR_CUDA(ctx, ctx->d_grid_items.reserve(g.items.size() + 1));
             RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_start.p, g.cell_start.data(), g.cell_start.size() * sizeof(uint32_t),
                                           cudaMemcpyHostToDevice, ctx->stream));
-            if (!g.items.empty())
+            RAR_CUDA(ctx, ctx->d_grid_geo.reserve(g.items.size() + 1));
+            if (!g.items.empty()) {
                 RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_items.p, g.items.data(), g.items.size() * sizeof(uint32_t),
                                               cudaMemcpyHostToDevice, ctx->stream));
+                RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_geo.p, g.item_geo.data(), g.items.size() * sizeof(f4),
+                                              cudaMemcpyHostToDevice, ctx->stream));
+            }
             RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
         ctx->grid_valid = true;
@@ -211,6 +216,7 @@ int attach_grid(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     a.grid.ny = g.ny;
     a.grid.cell_start = ctx->d_grid_start.p;
     a.grid.items = ctx->d_grid_items.p;
+    a.grid.item_geo = ctx->d_grid_geo.p;
     a.use_grid = 1;
     return RAR_OK;
 }
@@ -340,6 +346,7 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_listener_hists.release();
     ctx->d_grid_start.release();
     ctx->d_grid_items.release();
+    ctx->d_grid_geo.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RAR_OK;

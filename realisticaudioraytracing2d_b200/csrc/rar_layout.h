@@ -54,6 +54,7 @@ struct GridHost {
     float x0 = 0, y0 = 0, cw = 1, ch = 1;
     int nx = 0, ny = 0;
     std::vector<uint32_t> cell_start, items;
+    std::vector<f4> item_geo;  // endpoint record of items[i], so a cell's walls are one contiguous read
 };
 
 inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
@@ -72,7 +73,8 @@ inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
     const double pad = 1e-3 * std::max(maxx - minx, maxy - miny) + 1e-4;
     minx -= pad; miny -= pad; maxx += pad; maxy += pad;
     const double ex = maxx - minx, ey = maxy - miny;
-    const double target_cells = std::max(1.0, n / 2.0);
+    // 0.25 ... 2 cells per wall measured within 5 % of each other on the 10k-wall maze; 0.5 keeps the lists short
+    const double target_cells = std::max(1.0, n * 0.5);
     const double cell = std::sqrt(ex * ey / target_cells);
     const int nx = (int)std::min(2048.0, std::max(1.0, std::ceil(ex / cell)));
     const int ny = (int)std::min(2048.0, std::max(1.0, std::ceil(ey / cell)));
@@ -101,6 +103,15 @@ inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
                     if (pass == 0) count[cell_id + 1]++;
                     else g.items[g.cell_start[cell_id] + count[cell_id]++] = (uint32_t)w;
                 }
+            }
+        }
+        if (pass == 1) {
+            g.item_geo.resize(g.items.size());
+            for (size_t i = 0; i < g.items.size(); i++) {
+                const rar_segment &sgm = walls[g.items[i]];
+                volatile float ex = sgm.end[0] - sgm.start[0];  // the same rounded difference as split_walls()
+                volatile float ey = sgm.end[1] - sgm.start[1];
+                g.item_geo[i] = f4{sgm.start[0], sgm.start[1], ex, ey};
             }
         }
         if (pass == 0) {

@@ -130,6 +130,7 @@ struct GridView {
     int nx, ny;
     const uint32_t *cell_start;  // [nx * ny + 1]
     const uint32_t *items;       // wall indices, ascending within a cell
+    const f4 *item_geo;          // endpoint record {a.x, a.y, e.x, e.y} of items[i]
 };
 
 struct GridWalk {
@@ -198,10 +199,10 @@ RAR_HD void nearest_hit_grid(const Scene &sc, float ox, float oy, float dx, floa
             const int cell = w.iy * g.nx + w.ix;
             const uint32_t i0 = g.cell_start[cell], i1 = g.cell_start[cell + 1];
             for (uint32_t i = i0; i < i1; i++) {
-                const int k = (int)g.items[i];
-                const WallTest t = wall_test(sc.geo(k), ox, oy, dx, ndy);
+                const WallTest t = wall_test(sc.grid_geo(i), ox, oy, dx, ndy);
                 n_tests++;
                 if (wall_pass(t, closest_m)) {
+                    const int k = (int)g.items[i];
                     const float d = intersect_exact(t.num1, t.num2, t.dotP);
                     // cells are not visited in wall order: break ties by index like the ascending scan does
                     if (d < closest || (d == closest && d < kInf && k < hit)) {
@@ -236,7 +237,7 @@ RAR_HD bool check_vis_grid(const Scene &sc, float sx, float sy, float dx, float 
                 const int cell = w.iy * g.nx + w.ix;
                 const uint32_t i0 = g.cell_start[cell], i1 = g.cell_start[cell + 1];
                 for (uint32_t i = i0; i < i1; i++) {
-                    const WallTest t = wall_test(sc.geo((int)g.items[i]), sx, sy, dx, ndy);
+                    const WallTest t = wall_test(sc.grid_geo(i), sx, sy, dx, ndy);
                     n_tests++;
                     if (wall_pass(t, lim_m) && intersect_exact(t.num1, t.num2, t.dotP) < lim) {
                         blocked = true;

@@ -72,6 +72,10 @@ struct SceneView {
     int n, nb;
     GridView gv;
     __device__ __forceinline__ const GridView &grid() const { return gv; }
+    __device__ __forceinline__ f4 grid_geo(uint32_t i) const {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(gv.item_geo) + i);
+        return f4{v.x, v.y, v.z, v.w};
+    }
     __device__ __forceinline__ int n_walls() const { return n; }
     __device__ __forceinline__ f4 geo(int w) const {
         if (STAGE == 2) {

@@ -65,6 +65,8 @@ class RayTraceManager:
         self.obstacleObjects: List[GameObject] = []
         # [Header("Debug")] :31-34
         self.debugRayCount = 100
+        # not in the reference: wall count from which traces use RAR_FLAG_USE_GRID (results are identical)
+        self.gridThreshold = 64
         # private state :36-41
         self.activeSegments = None
         self.fullInputSamples = None
@@ -187,7 +189,9 @@ class RayTraceManager:
             source=self.source.position, listener=self.listener.position, listener_radius=self.listenerRadius,
             speed_of_sound=self.speedOfSound, input_gain=self.inputGain, max_bounce_count=self.maxBounces,
             rng_state_offset=self.frameCount, ray_count=self.rayCount, debug_ray_count=self.debugRayCount,
-            sample_rate=self.sampleRate, impulse_length=irLength)
+            sample_rate=self.sampleRate, impulse_length=irLength,
+            # large scenes: look walls up through the uniform grid (identical results)
+            flags=_capi.RAR_FLAG_USE_GRID if len(self.activeSegments) >= self.gridThreshold else 0)
         self._ctx.trace(p, slot)                                         # Trace + ProcessHits
         self.accumFrames += 1                                            # OnSimulationFinished :233
 

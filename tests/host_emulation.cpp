@@ -14,6 +14,7 @@ struct HostSceneT {
     static constexpr bool kGrid = GRID;
     rar::GridView gv;
     const rar::GridView &grid() const { return gv; }
+    rar::f4 grid_geo(uint32_t i) const { return gv.item_geo[i]; }
     const rar::f4 *g, *m0;
     const rar::f2 *m1;
     const float *ba;
@@ -72,7 +73,7 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
         rar::build_grid(walls, n, gh);
         if (gh.nx <= 0 || p->bands > 1) return -6;
         HostSceneT<true> sg;
-        sg.gv = rar::GridView{gh.x0, gh.y0, gh.cw, gh.ch, 1.0f / gh.cw, 1.0f / gh.ch, gh.nx, gh.ny, gh.cell_start.data(), gh.items.data()};
+        sg.gv = rar::GridView{gh.x0, gh.y0, gh.cw, gh.ch, 1.0f / gh.cw, 1.0f / gh.ch, gh.nx, gh.ny, gh.cell_start.data(), gh.items.data(), gh.item_geo.data()};
         sg.g = g.data(); sg.m0 = m0.data(); sg.m1 = m1.data(); sg.ba = band_abs; sg.n = n; sg.nb = p->bands;
         if (counting) run<1, true>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
         else run<1, false>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
