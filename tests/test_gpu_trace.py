@@ -312,3 +312,64 @@ def test_grid_mode_bundled_room_listeners_and_geometry_update(ctx, oracle):
         lx, ly = map(float, listeners[l])
         want = oracle.trace(oracle_walls(oracle, sc2.walls), oracle_params(oracle, dict(trace_kwargs(sc2), listener=(lx, ly)))).hist
         assert np.array_equal(ctx.ir_read_fixed(20 + l, n), want), l
+
+
+def _soup(seed, n, extent=50.0):
+    from realisticaudioraytracing2d_b200.host.scene_helper import SEGMENT_DTYPE
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0, extent, (n, 2)).astype(np.float32)
+    length = np.where(rng.random(n) < 0.1, rng.uniform(5, 40, n), rng.uniform(0.01, 2.0, n))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    b = (a + np.stack([np.cos(ang), np.sin(ang)], 1) * length[:, None]).astype(np.float32)
+    walls = np.zeros(n, dtype=SEGMENT_DTYPE)
+    walls["start"], walls["end"] = a, b
+    d = b - a
+    walls["normal"] = (np.stack([d[:, 1], -d[:, 0]], 1) / np.maximum(np.hypot(d[:, 0], d[:, 1]), 1e-9)[:, None]).astype(np.float32)
+    walls["absorption"] = rng.uniform(0.02, 0.4, n)
+    walls["scattering"] = rng.uniform(0, 1, n) * (rng.random(n) < 0.7)
+    walls["transmission"] = rng.uniform(0, 0.6, n) * (rng.random(n) < 0.5)
+    walls["ior"] = rng.uniform(0.3, 2.0, n)
+    return walls
+
+
+@pytest.mark.parametrize("seed,n", [(1, 37), (2, 700), (3, 3000)])
+def test_random_segment_soup_brute_and_grid(ctx, oracle, seed, n):
+    """Crossing, overlapping, tiny and long walls with per-wall random materials (refraction, jitter, diffuse
+    reflection, nested media): brute force, the grid and the oracle must agree bit for bit."""
+    sc = scenes.smoll_room()
+    sc.walls, sc.source, sc.listener = _soup(seed, n), (25.0, 25.0), (25.9, 25.4)
+    kw = trace_kwargs(sc, ray_count=20_000, max_bounce_count=16, impulse_length=48000)
+    want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw))
+    ctx.set_walls(sc.walls)
+    for flags in (_capi.RAR_FLAG_COUNT_TESTS, 0, _capi.RAR_FLAG_USE_GRID):
+        ctx.ir_clear(0, 48000, 1)
+        ctx.get_counters(reset=True)
+        ctx.trace(capi_params(_capi, dict(kw, flags=flags)), 0)
+        assert np.array_equal(ctx.ir_read_fixed(0, 48000), want.hist), flags
+        if flags == _capi.RAR_FLAG_COUNT_TESTS:
+            assert ctx.get_counters() == want.counters
+    assert np.count_nonzero(want.hist) >= 1 and want.counters["ray_bounces"] > 20_000
+
+
+def test_degenerate_inputs_match_the_oracle(ctx, oracle):
+    """Zero-length and duplicated walls, the source on a wall endpoint, a listener inside a wall, a tiny listener,
+    huge gain (fixed-point saturation path), slow sound (late arrivals dropped)."""
+    sc = scenes.smoll_room()
+    w = np.concatenate([sc.walls, sc.walls[:3], sc.walls[5:6]])
+    w["end"][20] = w["start"][20]                                  # zero-length wall
+    cases = [
+        dict(source=tuple(map(float, sc.walls["start"][0])), listener=sc.listener),       # source on an endpoint
+        dict(source=sc.source, listener=(0.0, 10.0)),                                     # listener inside the top wall
+        dict(source=sc.source, listener=sc.listener, listener_radius=1e-3),
+        dict(source=sc.source, listener=sc.listener, input_gain=1e9),
+        dict(source=sc.source, listener=sc.listener, speed_of_sound=3.0),
+        dict(source=(5.0, 3.0), listener=(5.0, 3.0)),                                     # listener at the source
+    ]
+    ctx.set_walls(w)
+    for i, over in enumerate(cases):
+        kw = trace_kwargs(sc, ray_count=4096, **over)
+        want = oracle.trace(oracle_walls(oracle, w), oracle_params(oracle, kw)).hist
+        for flags in (0, _capi.RAR_FLAG_USE_GRID):
+            ctx.ir_clear(0, kw["impulse_length"], 1)
+            ctx.trace(capi_params(_capi, dict(kw, flags=flags)), 0)
+            assert np.array_equal(ctx.ir_read_fixed(0, kw["impulse_length"]), want), (i, flags)
