@@ -466,6 +466,15 @@ RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<
     c.nee_candidate = 0;
     if (r.wall_depth != 0) return;
     const float wnx = c.m0.x, wny = c.m0.y;
+    if (!(COUNT && !p.count_executed)) {
+        // Cheap certificate that the estimate cannot clear the threshold, before the square root and the two
+        // reciprocals: cosT <= |normal| (1 + 1e-6) and totalD >= dist, so
+        //   contrib <= (E keep) 0.5 |n| / dist^2,
+        // compared in squared form with a 2 % margin, far above the few ulp of the literal evaluation below.
+        const float ek = (r.energy * c.keep) * 0.5f;
+        const float d2 = r.dist * r.dist;
+        if (ek <= 0.0f || (ek * ek) * dot2(wnx, wny, wnx, wny) < (0.96e-10f * d2) * d2) return;
+    }
     const float tlx = lx - r.px, tly = ly - r.py;
     const float dl = rar_sqrt(dot2(tlx, tly, tlx, tly));
     const bool flip = c.dir_dot_n > 0.0f;
