@@ -63,6 +63,8 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_ir_write(IntPtr ctx, int slot, [In] float[] ir, int impulseLength, int bands);
         [DllImport(Lib)] public static extern int rar_ir_device_ptr(IntPtr ctx, int slot, out IntPtr devicePtr, out long nWords);
 
+        [DllImport(Lib)] public static extern int rar_allreduce_slots([In] IntPtr[] contexts, int n, int slot);
+
         [DllImport(Lib)] public static extern int rar_trace(IntPtr ctx, ref RarTraceParams p, int slot);
         [DllImport(Lib)] public static extern int rar_trace_listeners(IntPtr ctx, ref RarTraceParams p, [In] float[] listenersXY, int nListeners, int firstSlot);
         [DllImport(Lib)] public static extern int rar_trace_hits(IntPtr ctx, ref RarTraceParams p, IntPtr hits, IntPtr keys, long capacity, out long count);

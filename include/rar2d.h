@@ -181,6 +181,14 @@ RAR_API int rar_ir_write(rar_context *ctx, int32_t slot, const float *ir, int32_
  * collective (one ncclAllReduce(sum, int64) across the GPUs that traced disjoint ray ranges). */
 RAR_API int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr, int64_t *n_words);
 
+/* Single-process multi-GPU hosts (a Unity process drives all GPUs itself): sums `slot` over n contexts, one per
+ * device, and leaves the total in every context's slot -- the all-reduce of the ray-range sharding, done by a
+ * kernel on the first context's device that reads the other devices' histograms directly over NVLink peer
+ * memory, followed by peer copies of the total.  All slots must have the same configuration.  Ordered after the
+ * work already enqueued on every context; asynchronous.  RAR_ERR_UNSUPPORTED when the devices cannot access
+ * each other's memory.  (One-process-per-GPU hosts use rar_ir_device_ptr with their own collective instead.) */
+RAR_API int rar_allreduce_slots(rar_context *const *ctxs, int32_t n, int32_t slot);
+
 /* ---- ray tracing ------------------------------------------------------------------------------ */
 
 /* RayTraceManager.cs:179-210 RunSimulation (Trace dispatch :205) fused with :220-232

@@ -65,6 +65,7 @@ SYMBOLS = {
     "rar_ir_read_fixed": (C.c_int, [_p, _i32, _p, _i64]),
     "rar_ir_write": (C.c_int, [_p, _i32, _p, _i32, _i32]),
     "rar_ir_device_ptr": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64)]),
+    "rar_allreduce_slots": (C.c_int, [C.POINTER(_p), _i32, _i32]),
     "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
     "rar_trace_listeners": (C.c_int, [_p, C.POINTER(TraceParams), _p, _i32, _i32]),
     "rar_trace_hits": (C.c_int, [_p, C.POINTER(TraceParams), _p, _p, _i64, C.POINTER(_i64)]),
@@ -271,6 +272,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.rar_launch_count(self._h))
+
+
+def allreduce_slots(contexts, slot: int) -> None:
+    """rar_allreduce_slots: sum `slot` over the contexts of this process (one per device), total everywhere."""
+    arr = (_p * len(contexts))(*[c._h for c in contexts])
+    check(contexts[0]._h, load().rar_allreduce_slots(arr, len(contexts), slot))
 
 
 class Convolver:

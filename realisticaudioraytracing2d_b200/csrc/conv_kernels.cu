@@ -77,6 +77,16 @@ __global__ void fixed_to_float_kernel(const long long *__restrict__ hist, float 
         out[i] = ((float)hist[i] * 9.094947017729282e-13f) * scale;
 }
 
+// All-reduce step of the single-process multi-GPU path: the root device sums its peers' histograms, read
+// straight from peer memory (NVLink P2P loads).
+__global__ void peer_reduce_kernel(long long *__restrict__ hist, const PeerHists peers, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long acc = hist[i];
+        for (int k = 0; k < peers.n; k++) acc += peers.p[k][i];
+        hist[i] = acc;
+    }
+}
+
 __global__ void float_to_fixed_kernel(const float *__restrict__ in, long long *__restrict__ hist, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         hist[i] = quantize_energy(in[i]);
@@ -310,6 +320,12 @@ void conv_init_tables() {
 cudaError_t launch_fixed_to_float(const long long *hist, float *out, long long n, float scale, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     fixed_to_float_kernel<<<min(blocks_for(n, 256), 4096), 256, 0, s>>>(hist, out, n, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_reduce(long long *hist, PeerHists peers, long long n, cudaStream_t s) {
+    if (n <= 0 || peers.n <= 0) return cudaSuccess;
+    peer_reduce_kernel<<<min(blocks_for(n, 256), 1184), 256, 0, s>>>(hist, peers, n);
     return cudaGetLastError();
 }
 

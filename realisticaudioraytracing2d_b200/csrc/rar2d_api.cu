@@ -495,6 +495,74 @@ int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr, int64_t
     return RAR_OK;
 }
 
+int rar_allreduce_slots(rar_context *const *ctxs, int32_t n, int32_t slot) {
+    if (!ctxs || n <= 0 || !ctxs[0]) return fail(nullptr, RAR_ERR_INVALID, "bad context array");
+    rar_context *root = ctxs[0];
+    if (n > 16) return fail(root, RAR_ERR_UNSUPPORTED, "at most 16 contexts");
+    Slot *S0 = get_slot(root, slot, false);
+    if (!S0 || !S0->configured) return fail(root, RAR_ERR_STATE, "slot is not configured on context 0");
+    const long long words = (long long)S0->impulse_length * S0->bands;
+    if (n == 1) return RAR_OK;
+    PeerHists peers;
+    peers.n = 0;
+    for (int i = 1; i < n; i++) {
+        rar_context *c = ctxs[i];
+        if (!c) return fail(root, RAR_ERR_INVALID, "null context in the array");
+        Slot *S = get_slot(c, slot, false);
+        if (!S || !S->configured || S->impulse_length != S0->impulse_length || S->bands != S0->bands)
+            return fail(root, RAR_ERR_INVALID, "slot configuration differs between contexts");
+        if (c->device != root->device) {
+            int can_rp = 0, can_pr = 0;
+            cudaDeviceCanAccessPeer(&can_rp, root->device, c->device);
+            cudaDeviceCanAccessPeer(&can_pr, c->device, root->device);
+            if (!can_rp || !can_pr) return fail(root, RAR_ERR_UNSUPPORTED, "devices cannot access each other's memory");
+        }
+        peers.p[peers.n++] = S->d_hist;
+        S->H_valid = false;
+    }
+    S0->H_valid = false;
+    // peer access root <-> others (idempotent)
+    for (int i = 1; i < n; i++) {
+        if (ctxs[i]->device == root->device) continue;
+        cudaSetDevice(root->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[i]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(root, RAR_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaSetDevice(ctxs[i]->device);
+        e = cudaDeviceEnablePeerAccess(root->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(root, RAR_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    // the root waits for every context's enqueued work
+    std::vector<cudaEvent_t> evs(n, nullptr);
+    cudaError_t e = cudaSuccess;
+    for (int i = 1; i < n && e == cudaSuccess; i++) {
+        cudaSetDevice(ctxs[i]->device);
+        e = cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(evs[i], ctxs[i]->stream);
+    }
+    cudaSetDevice(root->device);
+    for (int i = 1; i < n && e == cudaSuccess; i++) e = cudaStreamWaitEvent(root->stream, evs[i], 0);
+    if (e == cudaSuccess) e = launch_peer_reduce(S0->d_hist, peers, words, root->stream);
+    if (e == cudaSuccess) root->launches++;
+    // broadcast the total and make every context wait for its copy
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming);
+    for (int i = 1; i < n && e == cudaSuccess; i++) {
+        Slot *S = get_slot(ctxs[i], slot, false);
+        e = cudaMemcpyPeerAsync(S->d_hist, ctxs[i]->device, S0->d_hist, root->device, (size_t)words * sizeof(long long), root->stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(evs[0], root->stream);
+    for (int i = 1; i < n && e == cudaSuccess; i++) {
+        cudaSetDevice(ctxs[i]->device);
+        e = cudaStreamWaitEvent(ctxs[i]->stream, evs[0], 0);
+    }
+    for (int i = 0; i < n; i++)
+        if (evs[i]) cudaEventDestroy(evs[i]);  // destruction is deferred until the event has completed
+    cudaSetDevice(root->device);
+    RAR_CUDA(root, e);
+    return RAR_OK;
+}
+
 // ---- trace ------------------------------------------------------------------------------------------
 
 int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) {

@@ -57,6 +57,10 @@ struct ConvPlan {
 };
 
 // hist (Q23.40 int64) -> float, optionally scaled; n values.
+// hist[i] += sum over the peers' histograms (device pointers readable from the current device), i < n
+struct PeerHists { const long long *p[16]; int n; };
+cudaError_t launch_peer_reduce(long long *hist, PeerHists peers, long long n, cudaStream_t s);
+
 cudaError_t launch_fixed_to_float(const long long *hist, float *out, long long n, float scale, cudaStream_t s);
 cudaError_t launch_float_to_fixed(const float *in, long long *hist, long long n, cudaStream_t s);
 
