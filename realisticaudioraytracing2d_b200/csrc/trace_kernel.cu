@@ -18,6 +18,10 @@
 // Compiled with --fmad=false: the arithmetic contract of rar_math.cuh fixes every rounding.
 #include <cuda_runtime.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "rar_internal.h"
 
 namespace rar {
@@ -418,6 +422,32 @@ struct KernelChoice {
     int max_threads;
 };
 
+// cudaFuncSetAttribute + cudaOccupancyMaxActiveBlocksPerMultiprocessor cost microseconds each; a 15 000-ray
+// frame (config 1) runs for ~25 us, so the answers are remembered per (device, kernel, block size, smem).
+cudaError_t resident_blocks(const void *fn, int threads, size_t smem, int *blocks) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *, int, size_t>, int> cache;
+    static std::map<std::pair<int, const void *>, size_t> opted_in;  // largest dynamic smem enabled so far
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = opted_in[std::make_pair(dev, fn)];
+    if (smem > have) {  // the attribute is a per-kernel maximum: only ever raise it
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        have = smem;
+    }
+    const auto key = std::make_tuple(dev, fn, threads, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *blocks = it->second;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, fn, threads, smem);
+    if (e == cudaSuccess) cache[key] = *blocks;
+    return e;
+}
+
 // Small scenes (all planes in shared memory, several CTAs per SM): per-thread shadow walk, 256 threads.
 // Large scenes: warp-cooperative shadow rays; one CTA of 1024 threads per SM once the endpoint plane
 // takes more than half of shared memory.
@@ -491,7 +521,7 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
             k = count_tests ? KernelChoice{(const void *)trace_deposit_kernel<1, true, false, 2, 256, false, true>, 256}
                             : KernelChoice{(const void *)trace_deposit_kernel<1, false, false, 2, 256, false, true>, 256};
         smem = 16;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.max_threads, smem);
+        cudaError_t e = resident_blocks(k.fn, k.max_threads, smem, &per_sm);
         if (e != cudaSuccess) return e;
         best_resident = per_sm * k.max_threads;
     }
@@ -503,10 +533,8 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
         if (a.n_listeners > 0) kc = count_tests ? pick_listeners<true>(c.stage, c.big, coop) : pick_listeners<false>(c.stage, c.big, coop);
         else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, c.stage, c.big, coop)
                                : pick_mode<1>(count_tests, hits, c.stage, c.big, coop);
-        cudaError_t e = cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-        if (e != cudaSuccess) return e;
         int blocks = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kc.fn, kc.max_threads, c.smem);
+        cudaError_t e = resident_blocks(kc.fn, kc.max_threads, c.smem, &blocks);
         if (e != cudaSuccess) return e;
         const int resident = blocks * kc.max_threads;
         if (resident > best_resident) {
@@ -525,7 +553,7 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     if (!big_block) {
         while (threads > 64 && (n_rays + threads - 1) / threads < 2LL * dev.sm_count) threads >>= 1;
         if (threads != k.max_threads) {
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, threads, smem);
+            cudaError_t e = resident_blocks(k.fn, threads, smem, &per_sm);
             if (e != cudaSuccess) return e;
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         }
