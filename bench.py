@@ -248,7 +248,7 @@ def run_ours(args):
     kernel_ms = ms  # the step is clear + one trace kernel (+ all-reduce)
 
     # ---- end-to-end through the C-ABI with host buffers --------------------------------------------
-    ir_host = np.empty(n_bins, dtype=np.float32)
+    ir_host = torch.empty(n_bins, dtype=torch.float32).pin_memory()   # the caller's (pinned) result buffer
     walls_host = np.ascontiguousarray(sc.walls)
 
     def e2e_step(frame):
@@ -256,7 +256,7 @@ def run_ours(args):
         ctx.ir_clear(0, n_bins, 1)
         ctx.trace(params(frame), 0)
         sharding.allreduce_histogram(hist_t)
-        ir_host[:] = ctx.ir_read(0, n_bins)            # D2H: the float IR
+        ctx.ir_read_into(0, ir_host.data_ptr(), n_bins)   # D2H: the float IR
 
     for w in range(min(args.warmup, 3)):
         e2e_step(2000 + w)

@@ -197,6 +197,10 @@ class Context:
         self._ck(self._lib.rar_ir_read(self._h, slot, out.ctypes.data, n))
         return out
 
+    def ir_read_into(self, slot: int, host_ptr: int, n: int) -> None:
+        """rar_ir_read into caller-owned host memory (e.g. a pinned buffer), n floats."""
+        self._ck(self._lib.rar_ir_read(self._h, slot, _p(host_ptr), n))
+
     def ir_read_fixed(self, slot: int, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.int64)
         self._ck(self._lib.rar_ir_read_fixed(self._h, slot, out.ctypes.data, n))
