@@ -66,6 +66,7 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_allreduce_slots([In] IntPtr[] contexts, int n, int slot);
 
         [DllImport(Lib)] public static extern int rar_trace(IntPtr ctx, ref RarTraceParams p, int slot);
+        [DllImport(Lib)] public static extern int rar_trace_frames(IntPtr ctx, ref RarTraceParams p, int slot, int nFrames);
         [DllImport(Lib)] public static extern int rar_trace_listeners(IntPtr ctx, ref RarTraceParams p, [In] float[] listenersXY, int nListeners, int firstSlot);
         [DllImport(Lib)] public static extern int rar_trace_hits(IntPtr ctx, ref RarTraceParams p, IntPtr hits, IntPtr keys, long capacity, out long count);
         [DllImport(Lib)] public static extern int rar_get_counters(IntPtr ctx, out RarCounters c, int reset);

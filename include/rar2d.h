@@ -197,6 +197,12 @@ RAR_API int rar_allreduce_slots(rar_context *const *ctxs, int32_t n, int32_t slo
  * params->bands must match the slot's configuration. */
 RAR_API int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot);
 
+/* n_frames consecutive frames of the same dispatch (rng_state_offset, +1, ... +n_frames-1) accumulated into `slot`
+ * by ONE launch: what n_frames calls of rar_trace with successive Time.frameCount values produce (the per-chunk
+ * accumulation of RayTraceManager.cs:82,233, or the offline accumulation before RayTraceManagerComplex.BakeAudio),
+ * without n_frames launch latencies -- a 15 000-ray frame is too small to fill 148 SMs on its own.  Asynchronous. */
+RAR_API int rar_trace_frames(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames);
+
 /* BASELINE config 4 (batched auralisation): the same dispatch traced for n_listeners listener positions
  * (listeners_xy = x0,y0,x1,y1,...; params->listener_pos is ignored); listener l accumulates into slot
  * first_slot + l, each of which must be configured like `slot` of rar_trace.  The result in every slot is

@@ -67,6 +67,7 @@ SYMBOLS = {
     "rar_ir_device_ptr": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64)]),
     "rar_allreduce_slots": (C.c_int, [C.POINTER(_p), _i32, _i32]),
     "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
+    "rar_trace_frames": (C.c_int, [_p, C.POINTER(TraceParams), _i32, _i32]),
     "rar_trace_listeners": (C.c_int, [_p, C.POINTER(TraceParams), _p, _i32, _i32]),
     "rar_trace_hits": (C.c_int, [_p, C.POINTER(TraceParams), _p, _p, _i64, C.POINTER(_i64)]),
     "rar_get_counters": (C.c_int, [_p, C.POINTER(Counters), _i32]),
@@ -218,6 +219,9 @@ class Context:
     # trace ------------------------------------------------------------------------------------
     def trace(self, params: TraceParams, slot: int) -> None:
         self._ck(self._lib.rar_trace(self._h, C.byref(params), slot))
+
+    def trace_frames(self, params: TraceParams, slot: int, n_frames: int) -> None:
+        self._ck(self._lib.rar_trace_frames(self._h, C.byref(params), slot, n_frames))
 
     def trace_listeners(self, params: TraceParams, listeners_xy: np.ndarray, first_slot: int) -> None:
         xy = np.ascontiguousarray(listeners_xy, dtype=np.float32).reshape(-1, 2)

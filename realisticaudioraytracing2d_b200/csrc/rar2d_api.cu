@@ -565,7 +565,17 @@ int rar_allreduce_slots(rar_context *const *ctxs, int32_t n, int32_t slot) {
 
 // ---- trace ------------------------------------------------------------------------------------------
 
-int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) {
+static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames);
+
+int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) { return trace_frames_impl(ctx, params, slot, 1); }
+
+int rar_trace_frames(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames) {
+    if (n_frames < 0) return fail(ctx, RAR_ERR_INVALID, "n_frames must be >= 0");
+    if (n_frames == 0) return RAR_OK;
+    return trace_frames_impl(ctx, params, slot, n_frames);
+}
+
+static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames) {
     RAR_ENTER(ctx);
     int rc = check_trace_params(ctx, params);
     if (rc != RAR_OK) return rc;
@@ -578,6 +588,7 @@ int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) {
     rc = attach_grid(ctx, params, a);
     if (rc != RAR_OK) return rc;
     a.hist = reinterpret_cast<unsigned long long *>(S->d_hist);
+    a.n_frames = n_frames;
     const bool count = (params->flags & RAR_FLAG_COUNT_TESTS) != 0;
     a.counters = count ? ctx->d_counters.p : nullptr;
     if (params->debug_ray_count > 0) {

@@ -19,6 +19,7 @@ struct TraceLaunch {
     int bands;
     RayConsts p;
     long long ray_begin, ray_end;
+    int n_frames;  // >= 1: frames rng_state_offset .. +n_frames-1 of the same dispatch traced by one launch
     unsigned long long *hist;  // [impulse_length][bands] Q23.40, nullptr in hit-list mode
     rar_ray_info *hits;        // hit-list mode outputs
     rar_hit_key *keys;

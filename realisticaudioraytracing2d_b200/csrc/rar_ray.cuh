@@ -61,8 +61,8 @@ struct Arrival {
 
 // Raytrace2D.compute:51-61
 template <int BANDS>
-RAR_HD void ray_init(RayState<BANDS> &r, uint32_t id, const RayConsts &p) {
-    r.rng = id + p.rng_state_offset * 719393u;
+RAR_HD void ray_init(RayState<BANDS> &r, uint32_t id, const RayConsts &p, uint32_t frame = 0) {
+    r.rng = id + (p.rng_state_offset + frame) * 719393u;  // frame: extra frames batched into one launch
     float u = pcg_random(r.rng);
     float angle = rar_div((float)id + u, (float)p.ray_count) * 2.0f * kPi;
     sincos_poly(angle, r.dy, r.dx);

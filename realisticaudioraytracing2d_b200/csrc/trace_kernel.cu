@@ -255,22 +255,24 @@ __global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_consta
     const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
 
     const unsigned lane = threadIdx.x & 31u;
-    const long long n_rays = a.ray_end - a.ray_begin;
+    const long long rays_per_frame = a.ray_end - a.ray_begin;
+    const long long n_rays = rays_per_frame * a.n_frames;  // frames are laid out one after the other
     const int max_b = a.p.max_bounce_count;
     RayCounters ctr = {0, 0, 0, 0, 0};
 
     for (long long base = (long long)blockIdx.x * blockDim.x; base < n_rays; base += (long long)gridDim.x * blockDim.x) {
         const long long idx = base + threadIdx.x;
         bool alive = idx < n_rays;
-        const uint32_t id = (uint32_t)(a.ray_begin + idx);
+        const uint32_t frame = a.n_frames > 1 ? (uint32_t)(idx / rays_per_frame) : 0u;
+        const uint32_t id = (uint32_t)(a.ray_begin + (a.n_frames > 1 ? idx - (long long)frame * rays_per_frame : idx));
         RayState<BANDS> r;
-        if (alive) ray_init(r, id, a.p);
+        if (alive) ray_init(r, id, a.p, frame);
 
         // debugRays (Raytrace2D.compute:63,87,96): thread ids < 100 record wall hits (hard-coded in the shader),
         // ids < debugRayCount record the escape vertex.
         f4 *dbg = nullptr;
         int dbg_flags = 0;
-        if (a.debug_rays != nullptr && alive) {
+        if (a.debug_rays != nullptr && alive && frame == 0) {
             const long long row = (long long)id * (max_b + 1);
             dbg_flags = (id < 100u ? 1 : 0) | (id < (uint32_t)a.debug_ray_count ? 2 : 0);
             if (dbg_flags && row + max_b < a.debug_capacity) {
@@ -336,7 +338,8 @@ __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_cons
     const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
 
     const unsigned lane = threadIdx.x & 31u;
-    const long long n_rays = a.ray_end - a.ray_begin;
+    const long long rays_per_frame = a.ray_end - a.ray_begin;
+    const long long n_rays = rays_per_frame * a.n_frames;
     const int max_b = a.p.max_bounce_count;
     const int n_l = a.n_listeners;
     RayCounters ctr = {0, 0, 0, 0, 0};
@@ -344,9 +347,10 @@ __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_cons
     for (long long base = (long long)blockIdx.x * blockDim.x; base < n_rays; base += (long long)gridDim.x * blockDim.x) {
         const long long idx = base + threadIdx.x;
         bool alive = idx < n_rays;
-        const uint32_t id = (uint32_t)(a.ray_begin + idx);
+        const uint32_t frame = a.n_frames > 1 ? (uint32_t)(idx / rays_per_frame) : 0u;
+        const uint32_t id = (uint32_t)(a.ray_begin + (a.n_frames > 1 ? idx - (long long)frame * rays_per_frame : idx));
         RayState<BANDS> r;
-        if (alive) ray_init(r, id, a.p);
+        if (alive) ray_init(r, id, a.p, frame);
 
         for (int i = 0; i < max_b; i++) {
             if (!__any_sync(kFull, alive)) break;
@@ -485,7 +489,7 @@ KernelChoice pick_mode(bool count, bool hits, int stage, bool big, bool coop) {
 
 cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFacts &dev, cudaStream_t stream,
                          int *launches) {
-    const long long n_rays = a.ray_end - a.ray_begin;
+    const long long n_rays = (a.ray_end - a.ray_begin) * (a.n_frames > 1 ? a.n_frames : 1);
     if (n_rays <= 0 || a.p.max_bounce_count <= 0) return cudaSuccess;
     if (a.bands != 1 && a.bands != 8) return cudaErrorInvalidValue;
     if (a.n_listeners > 0 && (a.bands != 1 || a.hits != nullptr)) return cudaErrorInvalidValue;
@@ -564,6 +568,7 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     cudaError_t e;
 
     TraceLaunch arg = a;
+    if (arg.n_frames < 1) arg.n_frames = 1;
     void *params[] = {&arg};
     e = cudaLaunchKernel(k.fn, dim3(grid), dim3(threads), params, smem, stream);
     if (e == cudaSuccess && launches) ++*launches;

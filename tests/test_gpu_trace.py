@@ -390,3 +390,22 @@ def test_banded_layout_with_time_divisor(ctx, oracle):
     # band b of a bin never exceeds the broadband-equivalent ordering: lower absorption bands carry more energy
     e = got.reshape(6000, 8).sum(0)
     assert (e > 0).all()
+
+
+def test_trace_frames_equals_successive_frames(ctx, oracle):
+    """rar_trace_frames: n frames of the dispatch in one launch == n launches with successive rngStateOffset."""
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc, rng_state_offset=40, debug_ray_count=100)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace_frames(capi_params(_capi, kw), 0, 7)
+    hist = np.zeros(n, np.int64)
+    for f in range(40, 47):
+        oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, rng_state_offset=f)), hist=hist)
+    assert np.array_equal(ctx.ir_read_fixed(0, n), hist)
+    ctx.ir_clear(0, n, 1)
+    ctx.trace_frames(capi_params(_capi, kw), 0, 0)                  # zero frames: nothing
+    assert not ctx.ir_read_fixed(0, n).any()
+    with pytest.raises(_capi.RarError):
+        ctx.trace_frames(capi_params(_capi, kw), 0, -1)
