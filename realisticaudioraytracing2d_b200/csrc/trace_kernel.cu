@@ -250,7 +250,7 @@ __device__ __forceinline__ SceneView<STAGE, GRID> stage_scene(const TraceLaunch 
 // ---- the kernel -------------------------------------------------------------------------------------
 
 template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false>
-__global__ void __launch_bounds__(MAXT) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
+__global__ void __launch_bounds__(MAXT, (MAXT == 256 && BANDS == 1 && STAGE == 0 && !GRID) ? 4 : 0) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
 
