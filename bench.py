@@ -38,11 +38,11 @@ BOUNCES = 32
 FLOPS_PER_TEST = 20.0  # ~20 fp32 lane-ops per ray-segment test
 
 
-def _traffic(kernel: str):
-    """DRAM bytes per launch of a kernel, from the committed ncu capture (profiles/traffic.json), or None."""
+def _traffic(kernel: str, key: str = "bytes"):
+    """A per-launch figure of a kernel from the committed ncu capture (profiles/traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)[kernel]["bytes"]
+            return json.load(f)[kernel][key]
     except Exception:
         return None
 
@@ -335,6 +335,7 @@ def run_ours(args):
             "wall_ms_per_step_incl_flush": t_wall / len(frames) * 1e3,
             "roofline": {"bound": "fp32-issue", "achieved": ach, "peak": peak, "unit": "Tlaneop/s", "frac": ach / peak,
                          "traffic": _traffic("trace_deposit_kernel"), "kernel": "trace_deposit_kernel",
+                         "ncu_issue_slot_utilisation_pct": _traffic("trace_deposit_kernel", "sm_inst_issued_pct_of_peak"),
                          "note": f"{FLOPS_PER_TEST:g} fp32 lane-ops per ray-segment test (SURVEY 8d) x tests EXECUTED per launch / "
                                  "CUDA-event duration; peak = FFMA issue rate measured in this run (rar_measure_fp32_peak); "
                                  "HBM traffic is negligible for this kernel (scene 160 B, histogram 384 KB, L2 resident)"},
