@@ -29,6 +29,10 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+#ifndef RAR_GRID_MIN_BLOCKS
+#define RAR_GRID_MIN_BLOCKS 5
+#endif
+
 // ---- TMA / mbarrier primitives (PTX ISA 8.x, sm_90+) ------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -249,8 +253,19 @@ __device__ __forceinline__ SceneView<STAGE, GRID> stage_scene(const TraceLaunch 
 
 // ---- the kernel -------------------------------------------------------------------------------------
 
+// Resident CTAs per SM the register allocation is held to (0 = ptxas' own choice).  Measured on B200:
+//  * the headline small-scene variant is pinned at 64 registers (4 CTAs): an unpinned build once chose 73 and ran 3x slower;
+//  * the 8-band variants otherwise take ~105 registers (2 CTAs); at 64 with a few spills they run 20-30 % faster;
+//  * grid walks are latency-bound (dependent loads, divergent lanes) and like more warps still.
+constexpr int trace_min_blocks(int maxt, int bands, int stage, bool grid) {
+    if (maxt != 256) return 0;
+    if (grid) return RAR_GRID_MIN_BLOCKS;
+    if (bands == 8) return 4;
+    return (bands == 1 && stage == 0) ? 4 : 0;
+}
+
 template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false>
-__global__ void __launch_bounds__(MAXT, (MAXT == 256 && BANDS == 1 && STAGE == 0 && !GRID) ? 4 : 0) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
+__global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRID)) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
 
