@@ -547,6 +547,9 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     for (const Cand &c : cands) {
         if (a.use_grid) break;
         if (c.smem > budget) continue;
+        // The stage 1/2 kernels resolve shadow rays warp-cooperatively (one ray at a time), which is 3x slower than
+        // the per-thread walk on a handful of walls: small scenes always take stage 0, whatever the occupancy says.
+        if (a.n_walls < 128 && c.stage != 0) continue;
         const bool coop = c.stage != 0 || a.n_walls >= 128;
         KernelChoice kc;
         if (a.n_listeners > 0) kc = count_tests ? pick_listeners<true>(c.stage, c.big, coop) : pick_listeners<false>(c.stage, c.big, coop);
