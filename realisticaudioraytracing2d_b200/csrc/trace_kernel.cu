@@ -254,7 +254,8 @@ __device__ __forceinline__ SceneView<STAGE, GRID> stage_scene(const TraceLaunch 
 // ---- the kernel -------------------------------------------------------------------------------------
 
 // Resident CTAs per SM the register allocation is held to (0 = ptxas' own choice).  Measured on B200:
-//  * the headline small-scene variant is pinned at 64 registers (4 CTAs): an unpinned build once chose 73 and ran 3x slower;
+//  * the small-scene variant is pinned at 64 registers (4 CTAs/SM): 0.607 ms on config 2, against 0.645 ms at 76
+//    registers (3 CTAs) and 0.625 ms at 51 (5 CTAs, spills);
 //  * the 8-band variants otherwise take ~105 registers (2 CTAs); at 64 with a few spills they run 20-30 % faster;
 //  * grid walks are latency-bound (dependent loads, divergent lanes) and like more warps still.
 constexpr int trace_min_blocks(int maxt, int bands, int stage, bool grid) {
