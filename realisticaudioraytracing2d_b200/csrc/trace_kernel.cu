@@ -437,6 +437,8 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters) 
 
 // ---- launch selection -------------------------------------------------------------------------------
 
+constexpr int kCoopMinWalls = 256;  // from this many walls shadow rays are resolved warp-cooperatively
+
 struct KernelChoice {
     const void *fn;
     int max_threads;
@@ -549,9 +551,10 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
         if (a.use_grid) break;
         if (c.smem > budget) continue;
         // The stage 1/2 kernels resolve shadow rays warp-cooperatively (one ray at a time), which is 3x slower than
-        // the per-thread walk on a handful of walls: small scenes always take stage 0, whatever the occupancy says.
-        if (a.n_walls < 128 && c.stage != 0) continue;
-        const bool coop = c.stage != 0 || a.n_walls >= 128;
+        // the per-thread walk on a handful of walls (measured: per-thread wins at 64 and 128 walls, a tie at 256-1000,
+        // cooperative wins beyond): small scenes always take stage 0, whatever the occupancy says.
+        if (a.n_walls < kCoopMinWalls && c.stage != 0) continue;
+        const bool coop = c.stage != 0 || a.n_walls >= kCoopMinWalls;
         KernelChoice kc;
         if (a.n_listeners > 0) kc = count_tests ? pick_listeners<true>(c.stage, c.big, coop) : pick_listeners<false>(c.stage, c.big, coop);
         else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, c.stage, c.big, coop)
