@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--walls", type=int, default=2000)
     ap.add_argument("--compare", type=int, default=0)
     ap.add_argument("--count", action="store_true")
+    ap.add_argument("--grid", action="store_true", help="RAR_FLAG_USE_GRID: same histograms, far fewer tests")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -55,7 +56,10 @@ def main():
     for l in range(len(mine)):
         ctx.ir_clear(l, n, 1)
 
+    base_flags = _capi.RAR_FLAG_USE_GRID if a.grid else 0
+
     def prm(listener=(0.0, 0.0), flags=0, rays=a.rays):
+        flags |= base_flags
         return _capi.make_trace_params(sc.source, listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
                                        a.bounces, 1, rays, 0, sc.sample_rate, n, 1, 1.0, flags, 0, 0)
     ctx.trace_listeners(prm(rays=4096), mine[: min(2, len(mine))], 0)      # warm-up
@@ -76,7 +80,7 @@ def main():
     for l in range(len(mine)):
         h.update(ctx.ir_read_fixed(l, n).tobytes())
     out = {"config": f"config4: {a.walls}-wall scene, {len(all_listeners)} listeners, {a.rays} rays x {a.bounces} bounces each, 48000 bins",
-           "n_gpus": world, "listeners_per_gpu": len(mine), "fused_ms": float(ms[0]), "rank0_histograms_sha256": h.hexdigest()}
+           "n_gpus": world, "grid": bool(a.grid), "listeners_per_gpu": len(mine), "fused_ms": float(ms[0]), "rank0_histograms_sha256": h.hexdigest()}
     if a.count:
         k = min(len(mine), 16)
         base = len(mine) + 8
