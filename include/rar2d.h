@@ -105,7 +105,7 @@ typedef struct rar_trace_params {
     int32_t debug_ray_count;
     int32_t sample_rate;
     int32_t impulse_length;    /* number of time bins */
-    int32_t bands;             /* 1 = broadband; >1: slot layout IR[bin*bands + band] */
+    int32_t bands;             /* 1 = broadband; 2..128: slot layout IR[bin*bands + band] */
     float time_divisor;        /* 1: bin=(int)(t*SampleRate); W: bin=(int)(t*SampleRate/W) */
     uint32_t flags;            /* RAR_FLAG_* */
     int64_t ray_begin;         /* thread-id range [ray_begin, ray_end) traced by this call; */
@@ -155,8 +155,9 @@ RAR_API int rar_sync(rar_context *ctx);
  * planes).  n may be 0. */
 RAR_API int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n);
 
-/* Build extension for BASELINE config 3: per-wall absorption for `bands` frequency bands, row-major
- * [n][bands]; n must equal the current wall count. */
+/* Build extension for BASELINE config 3: per-wall absorption for `bands` frequency bands (2..128; the
+ * experimental variant's WindowSize default is 128, RayTraceManagerComplex.cs:27), row-major [n][bands]; n must
+ * equal the current wall count.  Slots of more than 8 bands are traced in chunks of 8 bands. */
 RAR_API int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int32_t n, int32_t bands);
 
 /* ---- impulse-response slots ------------------------------------------------------------------ */

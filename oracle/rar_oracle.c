@@ -255,7 +255,7 @@ static int check_vis(const trace_env *env, float sx, float sy, float ex, float e
     return 1;
 }
 
-#define ORC_MAX_BANDS 32
+#define ORC_MAX_BANDS 128
 
 /* Raytrace2D.compute:49-156 -- one thread of Trace. Band energies are the build's extension: band b
  * carries its own energy attenuated by band_abs[wall][b]; ray life, thresholds and branching follow

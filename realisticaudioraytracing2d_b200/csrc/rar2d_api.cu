@@ -171,7 +171,7 @@ int check_trace_params(rar_context *ctx, const rar_trace_params *p) {
     if (ctx->n_walls < 0) return fail(ctx, RAR_ERR_STATE, "rar_set_walls has not been called");
     if (p->ray_count <= 0) return fail(ctx, RAR_ERR_INVALID, "ray_count must be positive");
     if (p->max_bounce_count < 0) return fail(ctx, RAR_ERR_INVALID, "max_bounce_count must be >= 0");
-    if (p->bands != 1 && p->bands != 8) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 1 or 8");
+    if (p->bands < 1 || p->bands > 128) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 1..128");
     if (p->bands > 1 && (ctx->band_count != p->bands || ctx->band_rows != ctx->n_walls))
         return fail(ctx, RAR_ERR_STATE, "banded trace needs rar_set_wall_band_absorption for the current walls");
     if (p->impulse_length < 0 || p->sample_rate <= 0) return fail(ctx, RAR_ERR_INVALID, "bad impulse_length/sample_rate");
@@ -228,7 +228,10 @@ void fill_launch(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     a.mat1 = ctx->d_mat1.p;
     a.band_abs = p->bands > 1 ? ctx->d_band_abs.p : nullptr;
     a.n_walls = ctx->n_walls;
-    a.bands = p->bands;
+    a.bands = p->bands > 1 ? 8 : 1;  // banded slots are traced in chunks of 8 bands
+    a.band_total = p->bands;
+    a.band_offset = 0;
+    a.band_valid = p->bands > 8 ? 8 : p->bands;
     a.p = ray_consts(*p);
     ray_range(*p, a.ray_begin, a.ray_end);
 }
@@ -401,9 +404,9 @@ int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int3
     RAR_ENTER(ctx);
     if (ctx->n_walls < 0) return fail(ctx, RAR_ERR_STATE, "rar_set_walls has not been called");
     if (n != ctx->n_walls) return fail(ctx, RAR_ERR_INVALID, "row count must equal the wall count");
-    if (bands != 8) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 8");
+    if (bands < 2 || bands > 128) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 2..128");
     if (n > 0 && !absorption) return fail(ctx, RAR_ERR_INVALID, "null absorption table");
-    RAR_CUDA(ctx, ctx->d_band_abs.reserve((size_t)n * bands + 1));
+    RAR_CUDA(ctx, ctx->d_band_abs.reserve((size_t)n * bands + 16));  // a short last chunk of 8 reads past its row
     if (n > 0)
         RAR_CUDA(ctx, cudaMemcpy(ctx->d_band_abs.p, absorption, (size_t)n * bands * sizeof(float), cudaMemcpyHostToDevice));
     ctx->band_rows = n;
@@ -601,9 +604,19 @@ static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, i
         a.debug_ray_count = params->debug_ray_count;
         a.debug_capacity = (int)entries;
     }
-    int launched = 0;
-    RAR_CUDA(ctx, launch_trace(a, count, ctx->dev, ctx->stream, &launched));
-    ctx->launches += launched;
+    // A ray's path depends on the broadband material only, so a slot of more than 8 bands is filled by tracing the
+    // same rays once per chunk of 8 bands (tests are counted for the first chunk only).
+    for (int b0 = 0; b0 < params->bands; b0 += 8) {
+        a.band_offset = b0;
+        a.band_valid = params->bands - b0 < 8 ? params->bands - b0 : 8;
+        if (b0 > 0) {
+            a.counters = nullptr;
+            a.debug_rays = nullptr;
+        }
+        int launched = 0;
+        RAR_CUDA(ctx, launch_trace(a, count && b0 == 0, ctx->dev, ctx->stream, &launched));
+        ctx->launches += launched;
+    }
     S->H_valid = false;
     return RAR_OK;
 }

@@ -16,7 +16,10 @@ struct TraceLaunch {
     const f2 *mat1;         // [n_walls] transmission + ior
     const float *band_abs;  // [n_walls][bands] or nullptr
     int n_walls;
-    int bands;
+    int bands;        // bands the kernel instantiation carries: 1, or 8 (one chunk of a banded slot)
+    int band_total;   // bands of the slot (row stride of hist and of band_abs)
+    int band_offset;  // first band of this chunk
+    int band_valid;   // bands of this chunk that exist (<= 8)
     RayConsts p;
     long long ray_begin, ray_end;
     int n_frames;  // >= 1: frames rng_state_offset .. +n_frames-1 of the same dispatch traced by one launch

@@ -77,7 +77,7 @@ struct SceneView {
     const f4 *m0;
     const f2 *m1;
     const float *ba;
-    int n, nb;
+    int n, nb, boff;
     GridView gv;
     __device__ __forceinline__ const GridView &grid() const { return gv; }
     __device__ __forceinline__ f4 grid_geo(uint32_t i) const {
@@ -106,7 +106,9 @@ struct SceneView {
         }
         return m1[w];
     }
-    __device__ __forceinline__ const float *band_abs(int w) const { return ba + (size_t)w * nb; }
+    // row w of the [n][band_total] table, starting at this chunk's first band (the table is padded by 8 floats,
+    // so a short last chunk may read, and then ignore, a few values past its row)
+    __device__ __forceinline__ const float *band_abs(int w) const { return ba + (size_t)w * nb + boff; }
 };
 
 // ---- warp-aggregated fixed-point deposit ------------------------------------------------------------
@@ -138,9 +140,10 @@ __device__ __forceinline__ void deposit_hist(const TraceLaunch &a, unsigned long
         if (shared_bin) q = group_sum_q(peers, q);
         if (leader && q != 0) atomicAdd(hist + bin, (unsigned long long)q);
     } else {
-        unsigned long long *row = hist + (size_t)(valid ? bin : 0) * BANDS;
+        unsigned long long *row = hist + (size_t)(valid ? bin : 0) * a.band_total + a.band_offset;
 #pragma unroll
         for (int b = 0; b < BANDS; b++) {
+            if (b >= a.band_valid) break;  // short last chunk of a banded slot
             long long q = valid ? quantize_energy(h.band_e[b]) : 0;
             if (shared_bin) q = group_sum_q(peers, q);
             if (leader && q != 0) atomicAdd(row + b, (unsigned long long)q);
@@ -247,7 +250,8 @@ __device__ __forceinline__ SceneView<STAGE, GRID> stage_scene(const TraceLaunch 
     sc.m1 = STAGE == 0 ? s_mat1 : a.mat1;
     sc.ba = a.band_abs;
     sc.n = a.n_walls;
-    sc.nb = a.bands;
+    sc.nb = a.band_total;
+    sc.boff = a.band_offset;
     return sc;
 }
 
@@ -591,6 +595,11 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
 
     TraceLaunch arg = a;
     if (arg.n_frames < 1) arg.n_frames = 1;
+    if (arg.band_total < 1) {  // callers that do not chunk: the slot has exactly `bands` bands
+        arg.band_total = arg.bands;
+        arg.band_offset = 0;
+        arg.band_valid = arg.bands;
+    }
     void *params[] = {&arg};
     e = cudaLaunchKernel(k.fn, dim3(grid), dim3(threads), params, smem, stream);
     if (e == cudaSuccess && launches) ++*launches;

@@ -409,3 +409,22 @@ def test_trace_frames_equals_successive_frames(ctx, oracle):
     assert not ctx.ir_read_fixed(0, n).any()
     with pytest.raises(_capi.RarError):
         ctx.trace_frames(capi_params(_capi, kw), 0, -1)
+
+
+@pytest.mark.parametrize("bands", [2, 3, 20, 128])
+def test_arbitrary_band_counts_are_traced_in_chunks_of_eight(ctx, oracle, bands):
+    """Slots of any band count up to 128 (the experimental variant's WindowSize default): chunks of 8 bands, the
+    same rays per chunk; must equal the oracle's single pass."""
+    sc = scenes.maze(n_segments=300, ray_count=6000, max_bounces=10, bands=bands, seed=5)
+    kw = trace_kwargs(sc, bands=bands, impulse_length=6000, flags=_capi.RAR_FLAG_COUNT_TESTS)
+    ctx.set_walls(sc.walls)
+    ctx.set_wall_band_absorption(sc.band_absorption)
+    ctx.ir_clear(0, 6000, bands)
+    ctx.get_counters(reset=True)
+    ctx.trace(capi_params(_capi, kw), 0)
+    want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw), band_abs=sc.band_absorption)
+    assert np.array_equal(ctx.ir_read_fixed(0, 6000 * bands), want.hist) and np.count_nonzero(want.hist) > 100
+    assert ctx.get_counters() == want.counters                      # counted once, not once per chunk
+    ctx.ir_clear(0, 6000, bands)
+    ctx.trace(capi_params(_capi, dict(kw, flags=_capi.RAR_FLAG_USE_GRID)), 0)
+    assert np.array_equal(ctx.ir_read_fixed(0, 6000 * bands), want.hist)
