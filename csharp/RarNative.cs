@@ -1,6 +1,6 @@
 // RarNative.cs -- P/Invoke binding of librar2d (include/rar2d.h) for the Unity host.
 //
-// Drop this file and csharp/RayTraceManager.cs into Assets/Script/ (keeping the existing .meta of
+// Drop this file and csharp/RayTraceManager_rar2d.cs into Assets/Script/ (keeping the existing .meta of
 // RayTraceManager.cs so the scenes' script guid 2913e124... still resolves), and put librar2d.so in
 // Assets/Plugins/x86_64/.  Struct layouts are the reference's own: `Segment` is the 40-byte
 // LayoutKind.Sequential struct of Helpers/SceneHelper.cs:15-22 and is passed to rar_set_walls as is.

@@ -1,4 +1,4 @@
-// RayTraceManager.cs -- the live orchestrator component with its GPU work re-pointed at librar2d.
+// RayTraceManager_rar2d.cs (install as Assets/Script/RayTraceManager.cs) -- the live orchestrator component with its GPU work re-pointed at librar2d.
 //
 // Same serialized fields and Unity messages as the reference component (so existing scenes keep their
 // inspector values), different body: the ComputeShader/ComputeBuffer/AsyncGPUReadback plumbing is
