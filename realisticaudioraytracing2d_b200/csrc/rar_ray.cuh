@@ -1,14 +1,15 @@
 // rar_ray.cuh -- one ray of Raytrace2D.compute `Trace` (:49-156) as a per-bounce state machine.
 //
-// ray_init() + ray_bounce() are written once and used by the CUDA kernel (trace_kernel.cu); they
-// also compile as host C++ for tests/host_emulation.cpp.  A bounce returns up to two pending
-// arrivals (direct listener crossing, next-event estimate); the caller deposits them, which lets the
-// kernel do that with warp-convergent aggregation.
+// ray_init() and the bounce pieces (bounce_nearest, listener_direct, bounce_advance, listener_nee, the shadow
+// phase, nee_arrival, bounce_scatter) are written once and used by the CUDA kernels (trace_kernel.cu); they also
+// compile as host C++ for tests/host_emulation.cpp.  A bounce yields up to two pending arrivals (direct
+// listener crossing, next-event estimate); the caller deposits them, which lets the kernel do that with
+// warp-convergent aggregation.
 //
 // The inner loops over walls do NOT evaluate Common.hlsl:14-21 `intersect` literally.  They run a
-// division-free conservative filter and evaluate the literal formula (two correctly rounded
-// divisions and the original comparisons) only for the survivors, so the accepted hits and their
-// distances are bit-identical to the literal evaluation:
+// division-free conservative filter and evaluate the exact acceptance test (one correctly rounded division for
+// t1; t2 in [0,1] decided by sign and magnitude comparisons equivalent to comparing the rounded quotient) only
+// for the survivors, so the accepted hits and their distances are bit-identical to the literal evaluation:
 //   literal: dotP = dot(v2,v3); t1 = cross(v2,v1)/dotP; t2 = dot(v1,v3)/dotP;
 //            hit iff |dotP| >= eps, t1 >= eps, 0 <= t2 <= 1; nearest loop also needs t1 < closest.
 //   filter : with num1 = cross(v2,v1), num2 = dot(v1,v3), r = closest*(1+2^-20)*dotP
@@ -18,6 +19,9 @@
 //   hit the literal test accepts passes the filter.  The one literal-accepting case the filter does
 //   not see is t2 = num2/dotP underflowing to -0 for opposite signs, which needs |num2| < 2^-100 for
 //   any scene with coordinates below 2^50; HLSL flushes such values anyway.  ("filter".)
+//
+// Walls are scanned by brute force (the reference's algorithm and the measured mode) or, on request, looked up
+// through a uniform grid that visits a superset of the walls a query could accept (GridView below).
 #pragma once
 
 #include "rar_math.cuh"
