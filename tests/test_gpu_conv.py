@@ -150,3 +150,30 @@ def test_streaming_full_size_properties(ctx):
     for s in range(S):
         assert rel_l2(y[s, 5:], irs[s][: y.shape[1] - 5]) <= TOL
     cv.destroy()
+
+
+def test_streaming_config5_full_size_determinism_and_linearity(ctx):
+    """BASELINE config 5 at full size (256 streams x 480 000-tap IRs, 1875 partitions): the reduction order is
+    fixed, so two runs are bit-identical; and the convolver is linear in its input."""
+    S, B, n_ir = 256, 256, 480000
+    cv = _capi.Convolver(ctx, S, B, n_ir)
+    base = _ir(n_ir, seed=77)
+    for s in range(S):
+        cv.set_ir(s, np.roll(base, 37 * s))
+    rng = np.random.default_rng(8)
+    x1 = rng.uniform(-1, 1, (3, S, B)).astype(np.float32)
+    x2 = rng.uniform(-1, 1, (3, S, B)).astype(np.float32)
+
+    def run(x):
+        cv.reset()
+        return np.stack([cv.process(x[k]) for k in range(3)])
+
+    y1 = run(x1)
+    assert np.array_equal(run(x1), y1)                       # deterministic
+    y2, y12 = run(x2), run(x1 + x2)
+    assert rel_l2(y12, y1 + y2) <= 1e-5                      # linear
+    # first block of stream 0: plain convolution with the head of its IR
+    want = np.convolve(x1[0, 0].astype(np.float64), base[:B].astype(np.float64))[:B]
+    assert rel_l2(y1[0, 0], want) <= TOL
+    assert cv.bytes_per_block() > 1.9e9
+    cv.destroy()
