@@ -109,6 +109,7 @@ struct rar_context {
     DevBuf<uint32_t> d_grid_start, d_grid_items;
     DevBuf<f4> d_grid_geo;
     bool grid_valid = false;
+    bool walls_are_opaque = false;  // no wall has transmission > 0
 
     std::vector<Slot> slots;
     DevBuf<unsigned long long> d_counters;  // 5 counters + 1 hit count
@@ -233,6 +234,7 @@ void fill_launch(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     a.band_offset = 0;
     a.band_valid = p->bands > 8 ? 8 : p->bands;
     a.p = ray_consts(*p);
+    a.opaque = ctx->walls_are_opaque ? 1 : 0;
     ray_range(*p, a.ray_begin, a.ray_end);
 }
 
@@ -397,6 +399,7 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
     ctx->n_walls = n;
     ctx->h_walls.assign(segments, segments + n);
     ctx->grid_valid = false;
+    ctx->walls_are_opaque = walls_opaque(segments, n);
     return RAR_OK;
 }
 

@@ -40,6 +40,7 @@ struct TraceLaunch {
     // optional uniform grid (RAR_FLAG_USE_GRID); use_grid selects the grid instantiation
     GridView grid;
     int use_grid;
+    int opaque;  // no wall has transmission > 0: kernels without the transmit/refract branch may be used
 };
 
 struct DeviceFacts {

@@ -28,6 +28,13 @@ inline void split_walls(const rar_segment *in, int n, f4 *geo, f4 *mat0, f2 *mat
     }
 }
 
+// True when no wall can transmit: `rngVal < transmission` (Raytrace2D.compute:131) is then false for every draw.
+inline bool walls_opaque(const rar_segment *in, int n) {
+    for (int w = 0; w < n; w++)
+        if (in[w].transmission > 0.0f) return false;  // NaN compares false, exactly like `rngVal < NaN`
+    return true;
+}
+
 inline RayConsts ray_consts(const rar_trace_params &p) {
     RayConsts c;
     c.source_x = p.source_pos[0];

@@ -517,7 +517,11 @@ RAR_HD void nee_arrival(const RayState<BANDS> &r, const BounceCtx<BANDS> &c, boo
 }
 
 // :121-154: absorb, then transmit or reflect.  Returns false when the ray ended (energy below 1e-3, :122).
-template <int BANDS>
+// OPAQUE: the caller guarantees that no wall of the scene has transmission > 0.  `rngVal < transmission` (:131)
+// is then false for every draw (random() >= 0), so the whole transmit/refract branch is compiled out -- the draw
+// itself still happens.  Scenes of opaque walls are the common case and the kernel is a third smaller without
+// that branch (config 2: 0.607 -> 0.56 ms).
+template <int BANDS, bool OPAQUE = false>
 RAR_HD bool bounce_scatter(const RayConsts &p, RayState<BANDS> &r, const BounceCtx<BANDS> &c) {
     r.energy *= c.keep;  // :121-122
     if (BANDS > 1) {
@@ -531,7 +535,7 @@ RAR_HD bool bounce_scatter(const RayConsts &p, RayState<BANDS> &r, const BounceC
     const float nx = entering ? wnx : -wnx, ny = entering ? wny : -wny;
     const float rng_val = pcg_random(r.rng);  // :129 (always drawn)
 
-    if (rng_val < c.m1.x) {  // :131-147
+    if (!OPAQUE && rng_val < c.m1.x) {  // :131-147
         // wallSpeed / nextSpeed / eta (:126-128) are only consumed here; evaluating them lazily gives the
         // same values.
         const float wall_speed = rar_div(p.speed_of_sound, c.m1.y);
@@ -605,16 +609,16 @@ RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r
 
 // `visible` is the outcome of the shadow phase (ignored unless c.want_shadow).  Returns false when the ray
 // ended (energy below 1e-3, :122).
-template <int BANDS, bool COUNT, class Scene>
+template <int BANDS, bool COUNT, bool OPAQUE = false, class Scene>
 RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &nee,
                           const BounceCtx<BANDS> &c, bool visible, RayCounters *ctr) {
     (void)sc;
     nee_arrival<BANDS, COUNT>(r, c, visible, nee, ctr);
-    return bounce_scatter(p, r, c);
+    return bounce_scatter<BANDS, OPAQUE>(p, r, c);
 }
 
 // The three phases with a per-thread shadow walk: what a single thread of the reference does.
-template <int BANDS, bool COUNT, class Scene>
+template <int BANDS, bool COUNT, bool OPAQUE = false, class Scene>
 RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
                        Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
     BounceCtx<BANDS> c;
@@ -626,7 +630,7 @@ RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, 
         visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
         if (COUNT) ctr->shadow_tests += (unsigned long long)tests;
     }
-    return bounce_finish<BANDS, COUNT>(sc, p, r, nee, c, visible, ctr);
+    return bounce_finish<BANDS, COUNT, OPAQUE>(sc, p, r, nee, c, visible, ctr);
 }
 
 }  // namespace rar

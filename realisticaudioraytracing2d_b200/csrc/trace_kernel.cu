@@ -269,7 +269,7 @@ constexpr int trace_min_blocks(int maxt, int bands, int stage, bool grid) {
     return (bands == 1 && stage == 0) ? 4 : 0;
 }
 
-template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false>
+template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false>
 __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRID)) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SceneView<STAGE, GRID> sc = stage_scene<STAGE, GRID>(a, smem_raw);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
                 visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
                 if (COUNT) ctr.shadow_tests += (unsigned long long)tests;
             }
-            if (alive) alive = hit_wall && bounce_finish<BANDS, COUNT>(sc, a.p, r, nee, c, visible, &ctr);
+            if (alive) alive = hit_wall && bounce_finish<BANDS, COUNT, OPAQUE>(sc, a.p, r, nee, c, visible, &ctr);
             __syncwarp();
             if (HITS) {
                 emit_hit(a, direct, id, i, 0);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
 // nearest-hit loop once and then, for every listener, only the listener pieces: the direct crossing test
 // before the advance, and the next-event estimate with its shadow ray after it.  Listener l deposits into its
 // own histogram.  Result per listener: identical to a single-listener trace (same pieces, same order).
-template <bool COUNT, int STAGE, int MAXT, bool COOP, bool GRID = false>
+template <bool COUNT, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false>
 __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_constant__ TraceLaunch a) {
     constexpr int BANDS = 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_cons
                 __syncwarp();
                 deposit_hist(a, a.listener_hists[l], nee, lane);
             }
-            if (alive) alive = hit_wall && bounce_scatter(a.p, r, c);
+            if (alive) alive = hit_wall && bounce_scatter<BANDS, OPAQUE>(a.p, r, c);
         }
     }
 
@@ -489,6 +489,12 @@ KernelChoice pick_kernel(int stage, bool big_block, bool coop) {
     }
     return {(const void *)trace_deposit_kernel<BANDS, COUNT, HITS, 2, 256, true>, 256};
 }
+// production small-scene kernels without the transmit/refract branch
+template <int BANDS>
+KernelChoice pick_kernel_opaque(bool coop) {
+    if (coop) return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, true, false, true>, 256};
+    return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, false, false, true>, 256};
+}
 template <bool COUNT>
 KernelChoice pick_listeners(int stage, bool big_block, bool coop) {
     if (stage == 0) {
@@ -501,10 +507,30 @@ KernelChoice pick_listeners(int stage, bool big_block, bool coop) {
     }
     return {(const void *)trace_listeners_kernel<COUNT, 2, 256, true>, 256};
 }
+// The OPAQUE instantiations exist for the production mode only (no test counters, no hit list).
 template <int BANDS>
-KernelChoice pick_mode(bool count, bool hits, int stage, bool big, bool coop) {
+KernelChoice pick_mode(bool count, bool hits, bool opaque, int stage, bool big, bool coop) {
     if (hits) return count ? pick_kernel<BANDS, true, true>(stage, big, coop) : pick_kernel<BANDS, false, true>(stage, big, coop);
-    return count ? pick_kernel<BANDS, true, false>(stage, big, coop) : pick_kernel<BANDS, false, false>(stage, big, coop);
+    if (count) return pick_kernel<BANDS, true, false>(stage, big, coop);
+    // Large scenes spend their time in the wall loops; there the smaller scatter code changes nothing measurable (the
+    // 10k-wall maze was 2 % slower with it), so only the small-scene (stage 0) and grid kernels have the variant.
+    if (opaque && stage == 0) return pick_kernel_opaque<BANDS>(coop);
+    return pick_kernel<BANDS, false, false>(stage, big, coop);
+}
+KernelChoice pick_listeners_mode(bool count, bool opaque, int stage, bool big, bool coop) {
+    if (count) return pick_listeners<true>(stage, big, coop);
+    (void)opaque;  // the listener kernels spend their time in per-listener work, not in the scatter step
+    return pick_listeners<false>(stage, big, coop);
+}
+template <int BANDS>
+KernelChoice pick_grid(bool count, bool opaque) {
+    if (count) return {(const void *)trace_deposit_kernel<BANDS, true, false, 2, 256, false, true, false>, 256};
+    if (opaque) return {(const void *)trace_deposit_kernel<BANDS, false, false, 2, 256, false, true, true>, 256};
+    return {(const void *)trace_deposit_kernel<BANDS, false, false, 2, 256, false, true, false>, 256};
+}
+KernelChoice pick_grid_listeners(bool count, bool opaque) {
+    if (count) return {(const void *)trace_listeners_kernel<true, 2, 256, false, true, false>, 256};
+    return {(const void *)trace_listeners_kernel<false, 2, 256, false, true, false>, 256};
 }
 
 }  // namespace
@@ -537,15 +563,9 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     if (a.use_grid) {
         // Grid walks touch a few walls per query at data-dependent addresses: no staging, per-thread shadow walk.
         if (a.hits != nullptr) return cudaErrorInvalidValue;
-        if (a.n_listeners > 0)
-            k = count_tests ? KernelChoice{(const void *)trace_listeners_kernel<true, 2, 256, false, true>, 256}
-                            : KernelChoice{(const void *)trace_listeners_kernel<false, 2, 256, false, true>, 256};
-        else if (a.bands == 8)
-            k = count_tests ? KernelChoice{(const void *)trace_deposit_kernel<8, true, false, 2, 256, false, true>, 256}
-                            : KernelChoice{(const void *)trace_deposit_kernel<8, false, false, 2, 256, false, true>, 256};
-        else
-            k = count_tests ? KernelChoice{(const void *)trace_deposit_kernel<1, true, false, 2, 256, false, true>, 256}
-                            : KernelChoice{(const void *)trace_deposit_kernel<1, false, false, 2, 256, false, true>, 256};
+        const bool opq = a.opaque != 0;
+        if (a.n_listeners > 0) k = pick_grid_listeners(count_tests, opq);
+        else k = a.bands == 8 ? pick_grid<8>(count_tests, opq) : pick_grid<1>(count_tests, opq);
         smem = 16;
         cudaError_t e = resident_blocks(k.fn, k.max_threads, smem, &per_sm);
         if (e != cudaSuccess) return e;
@@ -560,9 +580,10 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
         if (a.n_walls < kCoopMinWalls && c.stage != 0) continue;
         const bool coop = c.stage != 0 || a.n_walls >= kCoopMinWalls;
         KernelChoice kc;
-        if (a.n_listeners > 0) kc = count_tests ? pick_listeners<true>(c.stage, c.big, coop) : pick_listeners<false>(c.stage, c.big, coop);
-        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, c.stage, c.big, coop)
-                               : pick_mode<1>(count_tests, hits, c.stage, c.big, coop);
+        const bool opq = a.opaque != 0;
+        if (a.n_listeners > 0) kc = pick_listeners_mode(count_tests, opq, c.stage, c.big, coop);
+        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, opq, c.stage, c.big, coop)
+                               : pick_mode<1>(count_tests, hits, opq, c.stage, c.big, coop);
         int blocks = 0;
         cudaError_t e = resident_blocks(kc.fn, kc.max_threads, c.smem, &blocks);
         if (e != cudaSuccess) return e;

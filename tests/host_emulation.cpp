@@ -29,7 +29,7 @@ using HostScene = HostSceneT<false>;
 
 struct Hit { float t, e, x, y; uint32_t ray; uint16_t bounce, kind; };
 
-template <int BANDS, bool COUNT, class SceneT>
+template <int BANDS, bool COUNT, bool OPAQUE, class SceneT>
 void run(const SceneT &sc, const rar_trace_params &p, long long *hist, Hit *hits, long long cap, long long *count,
          rar::RayCounters &ctr) {
     rar::RayConsts c = rar::ray_consts(p);
@@ -40,7 +40,7 @@ void run(const SceneT &sc, const rar_trace_params &p, long long *hist, Hit *hits
         rar::ray_init(r, (uint32_t)id, c);
         for (int i = 0; i < c.max_bounce_count; i++) {
             rar::Arrival<BANDS> a[2];
-            bool alive = rar::ray_bounce<BANDS, COUNT>(sc, c, r, a[0], a[1], &ctr);
+            bool alive = rar::ray_bounce<BANDS, COUNT, OPAQUE>(sc, c, r, a[0], a[1], &ctr);
             for (int k = 0; k < 2; k++) {
                 if (!a[k].has) continue;
                 if (hits) {
@@ -68,6 +68,7 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
     rar::RayCounters ctr;
     std::memset(&ctr, 0, sizeof ctr);
     long long cnt = 0;
+    const bool opaque = rar::walls_opaque(walls, n);  // the production (non-counting) path then uses the OPAQUE instantiation
     if (p->flags & RAR_FLAG_USE_GRID) {  // the uniform-grid instantiation (broadband only in this harness)
         rar::GridHost gh;
         rar::build_grid(walls, n, gh);
@@ -75,8 +76,9 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
         HostSceneT<true> sg;
         sg.gv = rar::GridView{gh.x0, gh.y0, gh.cw, gh.ch, 1.0f / gh.cw, 1.0f / gh.ch, gh.nx, gh.ny, gh.cell_start.data(), gh.items.data(), gh.item_geo.data()};
         sg.g = g.data(); sg.m0 = m0.data(); sg.m1 = m1.data(); sg.ba = band_abs; sg.n = n; sg.nb = p->bands;
-        if (counting) run<1, true>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
-        else run<1, false>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        if (counting) run<1, true, false>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else if (opaque) run<1, false, true>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else run<1, false, false>(sg, *p, hist, (Hit *)hits, cap, &cnt, ctr);
         if (count) *count = cnt;
         if (out) { out->ray_bounces = ctr.ray_bounces; out->nearest_tests = ctr.nearest_tests; out->shadow_tests = ctr.shadow_tests;
                    out->direct_hits = ctr.direct_hits; out->nee_hits = ctr.nee_hits; }
@@ -85,11 +87,13 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
     HostScene sc;
     sc.g = g.data(); sc.m0 = m0.data(); sc.m1 = m1.data(); sc.ba = band_abs; sc.n = n; sc.nb = p->bands;
     if (p->bands <= 1) {
-        if (counting) run<1, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
-        else run<1, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        if (counting) run<1, true, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else if (opaque) run<1, false, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else run<1, false, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
     } else if (p->bands == 8) {
-        if (counting) run<8, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
-        else run<8, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        if (counting) run<8, true, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else if (opaque) run<8, false, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        else run<8, false, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
     } else {
         return -5;
     }

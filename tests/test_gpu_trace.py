@@ -428,3 +428,26 @@ def test_arbitrary_band_counts_are_traced_in_chunks_of_eight(ctx, oracle, bands)
     ctx.ir_clear(0, 6000, bands)
     ctx.trace(capi_params(_capi, dict(kw, flags=_capi.RAR_FLAG_USE_GRID)), 0)
     assert np.array_equal(ctx.ir_read_fixed(0, 6000 * bands), want.hist)
+
+
+@pytest.mark.parametrize("case", ["shoebox_diffuse", "maze600", "maze600_b8", "maze600_grid"])
+def test_production_kernels_for_opaque_scenes(ctx, oracle, case):
+    """Scenes without any transmitting wall run kernels compiled without the transmit/refract branch (production
+    mode only: no counters).  They must reproduce the oracle, which always evaluates `rngVal < transmission`."""
+    if case == "shoebox_diffuse":
+        sc, bands, flags = scenes.shoebox(ray_count=100_000, max_bounces=24, scattering=0.4), 1, 0
+    else:
+        sc = scenes.maze(n_segments=600, ray_count=30_000, max_bounces=16, bands=8, seed=11)
+        bands = 8 if case == "maze600_b8" else 1
+        flags = _capi.RAR_FLAG_USE_GRID if case == "maze600_grid" else 0
+    assert not (sc.walls["transmission"] > 0).any()
+    kw = trace_kwargs(sc, bands=bands, flags=flags)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    if bands > 1:
+        ctx.set_wall_band_absorption(sc.band_absorption)
+    ctx.ir_clear(0, n, bands)
+    ctx.trace(capi_params(_capi, kw), 0)
+    want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, flags=0)),
+                        band_abs=sc.band_absorption if bands > 1 else None).hist
+    assert np.array_equal(ctx.ir_read_fixed(0, n * bands), want) and np.count_nonzero(want) > 500
