@@ -194,10 +194,23 @@ def run_ours(args):
         return _capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
                                        BOUNCES, frame, sc.ray_count, 100, sc.sample_rate, n_bins, 1, 1.0, flags, lo, hi)
 
-    def step(frame):
+    # The all-reduce of the ray-range sharding: the library's own kernel over CUDA-IPC peer memory (the process
+    # group only delivers the handles); RAR_BENCH_EXCHANGE=nccl selects ncclAllReduce on the same buffer instead.
+    use_nccl = os.environ.get("RAR_BENCH_EXCHANGE", "peer") == "nccl"
+    ex = sharding.PeerExchange(ctx, n_bins) if world > 1 else None
+
+    def exchange(nccl=use_nccl):
+        if world == 1:
+            return
+        if nccl:
+            sharding.allreduce_histogram(hist_t)
+        else:
+            ex.allreduce(0)
+
+    def step(frame, nccl=use_nccl):
         ctx.ir_clear(0, n_bins, 1)
         ctx.trace(params(frame), 0)
-        sharding.allreduce_histogram(hist_t)
+        exchange(nccl)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -247,6 +260,29 @@ def run_ours(args):
     ms = sum(a.elapsed_time(b) for a, b in evs)
     kernel_ms = ms  # the step is clear + one trace kernel (+ all-reduce)
 
+    # the same steps with the other all-reduce, for comparison (and a bit-for-bit check of the two)
+    exchange_compare = None
+    if world > 1:
+        ex.check()
+        other = []
+        for f in frames:
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step(f, not use_nccl)
+            e1.record(stream)
+            other.append((e0, e1))
+        barrier()
+        other_ms = sum(a.elapsed_time(b) for a, b in other)
+        step(frames[0], True)
+        torch.cuda.synchronize()
+        want = hist_t.clone()
+        step(frames[0], False)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(want, hist_t))
+        peer_ms, nccl_ms = (other_ms, ms) if use_nccl else (ms, other_ms)
+        exchange_compare = [peer_ms, nccl_ms, float(same)]
+
     # ---- end-to-end through the C-ABI with host buffers --------------------------------------------
     ir_host = torch.empty(n_bins, dtype=torch.float32).pin_memory()   # the caller's (pinned) result buffer
     walls_host = np.ascontiguousarray(sc.walls)
@@ -255,7 +291,7 @@ def run_ours(args):
         ctx.set_walls(walls_host)                      # H2D: 40 B per wall
         ctx.ir_clear(0, n_bins, 1)
         ctx.trace(params(frame), 0)
-        sharding.allreduce_histogram(hist_t)
+        exchange()
         ctx.ir_read_into(0, ir_host.data_ptr(), n_bins)   # D2H: the float IR
 
     for w in range(min(args.warmup, 3)):
@@ -272,6 +308,11 @@ def run_ours(args):
     if world > 1:
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        cmp_t = torch.tensor([exchange_compare[0], exchange_compare[1], -exchange_compare[2]], dtype=torch.float64, device=dev)
+        dist.all_reduce(cmp_t, op=dist.ReduceOp.MAX)
+        exchange_compare = {"peer_kernel_ms_per_step": float(cmp_t[0]) / len(frames),
+                            "nccl_ms_per_step": float(cmp_t[1]) / len(frames),
+                            "bit_identical": bool(float(cmp_t[2]) == -1.0)}
         sm = tt.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms, tests_all, tests_exec_all = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
@@ -324,7 +365,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_total": RAYS_PER_GPU * world, "bounces": BOUNCES, "walls": 4,
                        "ir_bins": n_bins, "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed",
-                       "exchange": "ncclAllReduce(sum,int64) of the histogram" if world > 1 else "none"},
+                       "exchange": "none" if world == 1 else
+                                   ("ncclAllReduce(sum,int64) of the histogram" if use_nccl else
+                                    "all-reduce(sum,int64) of the histogram by the library's peer-memory kernel "
+                                    "(CUDA IPC over NVLink, one launch per rank)")},
             "ir_build_ms": ms / len(frames),
             "tests_per_step": tests_all / len(frames),
             "tests_executed_per_step": tests_exec_all / len(frames),
@@ -347,9 +391,12 @@ def run_ours(args):
             "device": info,
             "peaks": {"kind": peaks_kind, "hbm_gbs": peaks.get("hbm_gbs"), "fp32_laneops_per_s_measured": fp32_peak},
         }
+        if exchange_compare:
+            line["exchange_compare"] = exchange_compare
         line.update(extra)
         _emit(line)
     if world > 1:
+        ex.close()
         dist.barrier()
         dist.destroy_process_group()
     ctx.destroy()

@@ -64,6 +64,12 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_ir_device_ptr(IntPtr ctx, int slot, out IntPtr devicePtr, out long nWords);
 
         [DllImport(Lib)] public static extern int rar_allreduce_slots([In] IntPtr[] contexts, int n, int slot);
+        // one process per GPU: all-reduce kernel over CUDA-IPC peer memory (handles are 80 bytes each)
+        [DllImport(Lib)] public static extern int rar_exchange_create(IntPtr ctx, long capacityWords, [Out] byte[] handle);
+        [DllImport(Lib)] public static extern int rar_exchange_connect(IntPtr ctx, int rank, int world, [In] byte[] handles);
+        [DllImport(Lib)] public static extern int rar_exchange_allreduce(IntPtr ctx, int slot, int mode);
+        [DllImport(Lib)] public static extern int rar_exchange_status(IntPtr ctx);
+        [DllImport(Lib)] public static extern int rar_exchange_destroy(IntPtr ctx);
 
         [DllImport(Lib)] public static extern int rar_trace(IntPtr ctx, ref RarTraceParams p, int slot);
         [DllImport(Lib)] public static extern int rar_trace_frames(IntPtr ctx, ref RarTraceParams p, int slot, int nFrames);

@@ -190,6 +190,35 @@ RAR_API int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr,
  * each other's memory.  (One-process-per-GPU hosts use rar_ir_device_ptr with their own collective instead.) */
 RAR_API int rar_allreduce_slots(rar_context *const *ctxs, int32_t n, int32_t slot);
 
+/* One-process-per-GPU hosts (torchrun-style): the same all-reduce as ONE kernel per rank over NVLink peer
+ * memory, with no collective library on the data path.  Every rank owns an exchange region (flag table + staging
+ * buffers) that the other processes map through CUDA IPC; the kernel stages the local histogram, meets its peers
+ * at a flag barrier in peer memory, sums the ranks' staged histograms straight out of their HBM and leaves the
+ * total in the slot (one-shot: every rank reads everything; two-shot: each rank reduces one slice and scatters
+ * the totals).  Integer sums: the result is bit-identical to rar_allreduce_slots, to ncclAllReduce over
+ * rar_ir_device_ptr, and to an unsharded trace.
+ *
+ *   rar_exchange_create   allocates the region for histograms of up to capacity_words words and writes the
+ *                         RAR_EXCHANGE_HANDLE_BYTES-byte handle the host must deliver to every other rank
+ *                         (any transport: torch.distributed all_gather, MPI, a pipe).  Blocking.
+ *   rar_exchange_connect  `handles` = world handles in rank order (this rank's own included); maps the peers'
+ *                         regions.  Every rank must have created its region first.  Blocking.
+ *   rar_exchange_allreduce enqueues the kernel on the context's stream after the work already there; every
+ *                         rank must call it the same number of times with the same slot configuration and mode
+ *                         (RAR_EXCHANGE_AUTO picks one-shot up to 512 KiB).  world == 1 is a no-op.
+ *   rar_exchange_status   waits for the stream and returns RAR_ERR_STATE if a peer failed to reach a barrier
+ *                         within the time limit (5 s) -- the kernel gives up instead of spinning forever.
+ *   rar_exchange_destroy  unmaps and frees; the host must make sure no peer is still inside a call (a process
+ *                         barrier).  Also done by rar_destroy. */
+#define RAR_EXCHANGE_HANDLE_BYTES 80
+#define RAR_EXCHANGE_MAX_RANKS 16
+enum { RAR_EXCHANGE_AUTO = 0, RAR_EXCHANGE_ONE_SHOT = 1, RAR_EXCHANGE_TWO_SHOT = 2 };
+RAR_API int rar_exchange_create(rar_context *ctx, int64_t capacity_words, void *handle_out);
+RAR_API int rar_exchange_connect(rar_context *ctx, int32_t rank, int32_t world, const void *handles);
+RAR_API int rar_exchange_allreduce(rar_context *ctx, int32_t slot, int32_t mode);
+RAR_API int rar_exchange_status(rar_context *ctx);
+RAR_API int rar_exchange_destroy(rar_context *ctx);
+
 /* ---- ray tracing ------------------------------------------------------------------------------ */
 
 /* RayTraceManager.cs:179-210 RunSimulation (Trace dispatch :205) fused with :220-232

@@ -18,6 +18,9 @@ RAR_FLAG_EXACT_RAY_COUNT = 1
 RAR_FLAG_COUNT_TESTS = 2
 RAR_FLAG_COUNT_EXECUTED = 4
 RAR_FLAG_USE_GRID = 8
+RAR_EXCHANGE_HANDLE_BYTES = 80
+RAR_EXCHANGE_MAX_RANKS = 16
+RAR_EXCHANGE_AUTO, RAR_EXCHANGE_ONE_SHOT, RAR_EXCHANGE_TWO_SHOT = 0, 1, 2
 
 # include/rar2d.h rar_segment / rar_ray_info / rar_hit_key
 SEGMENT_DTYPE = np.dtype(
@@ -66,6 +69,11 @@ SYMBOLS = {
     "rar_ir_write": (C.c_int, [_p, _i32, _p, _i32, _i32]),
     "rar_ir_device_ptr": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64)]),
     "rar_allreduce_slots": (C.c_int, [C.POINTER(_p), _i32, _i32]),
+    "rar_exchange_create": (C.c_int, [_p, _i64, _p]),
+    "rar_exchange_connect": (C.c_int, [_p, _i32, _i32, _p]),
+    "rar_exchange_allreduce": (C.c_int, [_p, _i32, _i32]),
+    "rar_exchange_status": (C.c_int, [_p]),
+    "rar_exchange_destroy": (C.c_int, [_p]),
     "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
     "rar_trace_frames": (C.c_int, [_p, C.POINTER(TraceParams), _i32, _i32]),
     "rar_trace_listeners": (C.c_int, [_p, C.POINTER(TraceParams), _p, _i32, _i32]),
@@ -215,6 +223,27 @@ class Context:
         ptr, n = _p(), _i64()
         self._ck(self._lib.rar_ir_device_ptr(self._h, slot, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
+
+    # multi-process peer-memory all-reduce -------------------------------------------------------
+    def exchange_create(self, capacity_words: int) -> bytes:
+        buf = C.create_string_buffer(RAR_EXCHANGE_HANDLE_BYTES)
+        self._ck(self._lib.rar_exchange_create(self._h, capacity_words, buf))
+        return buf.raw
+
+    def exchange_connect(self, rank: int, world: int, handles) -> None:
+        blob = b"".join(handles)
+        if len(blob) != world * RAR_EXCHANGE_HANDLE_BYTES:
+            raise ValueError("need one %d-byte handle per rank" % RAR_EXCHANGE_HANDLE_BYTES)
+        self._ck(self._lib.rar_exchange_connect(self._h, rank, world, blob))
+
+    def exchange_allreduce(self, slot: int, mode: int = RAR_EXCHANGE_AUTO) -> None:
+        self._ck(self._lib.rar_exchange_allreduce(self._h, slot, mode))
+
+    def exchange_status(self) -> None:
+        self._ck(self._lib.rar_exchange_status(self._h))
+
+    def exchange_destroy(self) -> None:
+        self._ck(self._lib.rar_exchange_destroy(self._h))
 
     # trace ------------------------------------------------------------------------------------
     def trace(self, params: TraceParams, slot: int) -> None:

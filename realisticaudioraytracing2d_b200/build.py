@@ -24,6 +24,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 UNITS = [
     ("trace_kernel.cu", ["--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
     ("conv_kernels.cu", []),
+    ("exchange_kernel.cu", []),
     ("rar2d_api.cu", []),
 ]
 HEADERS = ["rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_layout.h", "rar_internal.h", "../../include/rar2d.h"]

@@ -86,6 +86,28 @@ struct Ticket {
     DevBuf<float2> d_X, d_Y;
 };
 
+// Exchange region of the multi-process peer-memory all-reduce (exchange_kernel.cu):
+//   [flag table][status + padding][in 0][in 1][out 0][out 1], each buffer stage_bytes long.
+struct Exchange {
+    char *region = nullptr;
+    size_t region_bytes = 0, stage_bytes = 0;
+    long long cap_words = 0;
+    bool connected = false;
+    int rank = 0, world = 1;
+    unsigned epoch = 0;
+    void *opened[kExMaxRanks] = {};  // bases returned by cudaIpcOpenMemHandle (to close)
+    char *peer[kExMaxRanks] = {};    // every rank's region as addressable from this process
+};
+constexpr size_t kExHeaderBytes = kExFlagWords * sizeof(unsigned) + 256;
+
+struct ExchangeHandle {  // RAR_EXCHANGE_HANDLE_BYTES
+    cudaIpcMemHandle_t mem;
+    unsigned long long offset;     // of the region inside the IPC allocation
+    unsigned long long cap_words;
+};
+static_assert(sizeof(ExchangeHandle) == RAR_EXCHANGE_HANDLE_BYTES, "exchange handle layout");
+static_assert(kExMaxRanks == RAR_EXCHANGE_MAX_RANKS, "rank limit");
+
 }  // namespace
 
 struct rar_context {
@@ -120,6 +142,7 @@ struct rar_context {
     DevBuf<unsigned long long *> d_listener_hists;
     std::vector<Ticket *> tickets;
     std::vector<rar_convolver *> convolvers;
+    Exchange ex;
 };
 
 struct rar_convolver {
@@ -334,6 +357,7 @@ int rar_destroy(rar_context *ctx) {
     if (!ctx) return RAR_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rar_exchange_destroy(ctx);
     while (!ctx->convolvers.empty()) rar_conv_destroy(ctx->convolvers.back());
     for (Ticket *t : ctx->tickets) free_ticket(t);
     for (Slot &s : ctx->slots) {
@@ -566,6 +590,140 @@ int rar_allreduce_slots(rar_context *const *ctxs, int32_t n, int32_t slot) {
         if (evs[i]) cudaEventDestroy(evs[i]);  // destruction is deferred until the event has completed
     cudaSetDevice(root->device);
     RAR_CUDA(root, e);
+    return RAR_OK;
+}
+
+// ---- multi-process peer-memory all-reduce -------------------------------------------------------------
+
+int rar_exchange_destroy(rar_context *ctx) {
+    RAR_ENTER(ctx);
+    Exchange &X = ctx->ex;
+    if (!X.region) return RAR_OK;
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < kExMaxRanks; r++)
+        if (X.opened[r]) cudaIpcCloseMemHandle(X.opened[r]);
+    cudaFree(X.region);
+    cudaGetLastError();
+    X = Exchange();
+    return RAR_OK;
+}
+
+int rar_exchange_create(rar_context *ctx, int64_t capacity_words, void *handle_out) {
+    RAR_ENTER(ctx);
+    if (capacity_words <= 0 || !handle_out) return fail(ctx, RAR_ERR_INVALID, "bad capacity/handle");
+    int rc = rar_exchange_destroy(ctx);
+    if (rc != RAR_OK) return rc;
+    Exchange &X = ctx->ex;
+    X.stage_bytes = (((size_t)capacity_words + 2) * sizeof(long long) + 255) & ~(size_t)255;
+    size_t bytes = kExHeaderBytes + 4 * X.stage_bytes;
+    bytes = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);  // whole 2 MiB pages: an allocation of its own
+    RAR_CUDA(ctx, cudaMalloc((void **)&X.region, bytes));
+    X.region_bytes = bytes;
+    X.cap_words = capacity_words;
+    cudaError_t e = cudaMemsetAsync(X.region, 0, bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ExchangeHandle h;
+    std::memset(&h, 0, sizeof h);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h.mem, X.region);
+    if (e != cudaSuccess) {
+        cudaFree(X.region);
+        X = Exchange();
+        RAR_CUDA(ctx, e);
+    }
+    // The handle names the allocation the driver carved the region from; ship the region's offset in it.
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    unsigned long long base = 0;
+    size_t span = 0;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
+        ((range_fn)fn)(&base, &span, (unsigned long long)(uintptr_t)X.region) == 0 && base)
+        h.offset = (unsigned long long)(uintptr_t)X.region - base;
+    cudaGetLastError();
+    h.cap_words = (unsigned long long)capacity_words;
+    std::memcpy(handle_out, &h, sizeof h);
+    return RAR_OK;
+}
+
+int rar_exchange_connect(rar_context *ctx, int32_t rank, int32_t world, const void *handles) {
+    RAR_ENTER(ctx);
+    Exchange &X = ctx->ex;
+    if (!X.region) return fail(ctx, RAR_ERR_STATE, "rar_exchange_create has not been called");
+    if (X.connected) return fail(ctx, RAR_ERR_STATE, "exchange is already connected (destroy it first)");
+    if (world < 1 || world > kExMaxRanks || rank < 0 || rank >= world || !handles)
+        return fail(ctx, RAR_ERR_INVALID, "bad rank/world/handles (at most 16 ranks)");
+    const ExchangeHandle *hs = static_cast<const ExchangeHandle *>(handles);
+    for (int r = 0; r < world; r++) {
+        ExchangeHandle h;
+        std::memcpy(&h, hs + r, sizeof h);
+        if ((long long)h.cap_words != X.cap_words) return fail(ctx, RAR_ERR_INVALID, "exchange capacity differs between ranks");
+        if (r == rank) {
+            X.peer[r] = X.region;
+            continue;
+        }
+        void *base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h.mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int k = 0; k < r; k++)
+                if (X.opened[k]) {
+                    cudaIpcCloseMemHandle(X.opened[k]);
+                    X.opened[k] = nullptr;
+                }
+            std::string m = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+            return fail(ctx, e == cudaErrorPeerAccessUnsupported ? RAR_ERR_UNSUPPORTED : RAR_ERR_CUDA, "%s", m.c_str());
+        }
+        X.opened[r] = base;
+        X.peer[r] = static_cast<char *>(base) + h.offset;
+    }
+    X.rank = rank;
+    X.world = world;
+    X.epoch = 0;
+    X.connected = true;
+    return RAR_OK;
+}
+
+int rar_exchange_allreduce(rar_context *ctx, int32_t slot, int32_t mode) {
+    RAR_ENTER(ctx);
+    Exchange &X = ctx->ex;
+    if (!X.connected) return fail(ctx, RAR_ERR_STATE, "exchange is not connected");
+    Slot *S = get_slot(ctx, slot, false);
+    if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
+    if (mode < RAR_EXCHANGE_AUTO || mode > RAR_EXCHANGE_TWO_SHOT) return fail(ctx, RAR_ERR_INVALID, "bad exchange mode");
+    const long long words = (long long)S->impulse_length * S->bands;
+    if (words > X.cap_words) return fail(ctx, RAR_ERR_INVALID, "slot is larger than the exchange capacity");
+    if (X.world == 1 || words == 0) return RAR_OK;
+    ExchangeLaunch a;
+    std::memset(&a, 0, sizeof a);
+    a.hist = S->d_hist;
+    a.n_vecs = (words + 1) / 2;
+    a.slice_vecs = (a.n_vecs + X.world - 1) / X.world;
+    a.rank = X.rank;
+    a.world = X.world;
+    a.epoch = ++X.epoch;
+    a.two_shot = mode == RAR_EXCHANGE_TWO_SHOT || (mode == RAR_EXCHANGE_AUTO && words * 8 > (512 << 10));
+    const size_t parity = a.epoch & 1u;
+    for (int r = 0; r < X.world; r++) {
+        a.flags[r] = reinterpret_cast<unsigned *>(X.peer[r]);
+        a.stage_in[r] = reinterpret_cast<long long *>(X.peer[r] + kExHeaderBytes + parity * X.stage_bytes);
+        a.stage_out[r] = reinterpret_cast<long long *>(X.peer[r] + kExHeaderBytes + (2 + parity) * X.stage_bytes);
+    }
+    a.status = reinterpret_cast<unsigned *>(X.region + kExFlagWords * sizeof(unsigned));
+    a.timeout_ns = 5000000000ull;
+    RAR_CUDA(ctx, launch_exchange_allreduce(a, ctx->stream));
+    ctx->launches++;
+    S->H_valid = false;
+    return RAR_OK;
+}
+
+int rar_exchange_status(rar_context *ctx) {
+    RAR_ENTER(ctx);
+    Exchange &X = ctx->ex;
+    if (!X.region) return fail(ctx, RAR_ERR_STATE, "rar_exchange_create has not been called");
+    unsigned st = 0;
+    RAR_CUDA(ctx, cudaMemcpyAsync(&st, X.region + kExFlagWords * sizeof(unsigned), sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (st) return fail(ctx, RAR_ERR_STATE, "a peer did not reach the exchange barrier within the time limit");
     return RAR_OK;
 }
 

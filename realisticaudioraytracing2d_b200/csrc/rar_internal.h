@@ -66,6 +66,25 @@ struct ConvPlan {
 struct PeerHists { const long long *p[16]; int n; };
 cudaError_t launch_peer_reduce(long long *hist, PeerHists peers, long long n, cudaStream_t s);
 
+// exchange_kernel.cu -- multi-process all-reduce of a histogram over CUDA-IPC-mapped peer memory
+constexpr int kExMaxRanks = 16;
+constexpr int kExMaxBlocks = 296;  // two per SM
+constexpr size_t kExFlagWords = 2 * (size_t)kExMaxBlocks * kExMaxRanks;  // u32 words of the flag table
+struct ExchangeLaunch {
+    long long *hist;        // this rank's slot
+    long long n_vecs;       // 16-byte vectors covering the slot's words
+    long long slice_vecs;   // vectors per rank slice (two-shot), world * slice_vecs >= n_vecs
+    int rank, world;
+    unsigned epoch;         // number of this call, >= 1, the same on every rank
+    int two_shot;
+    unsigned *flags[kExMaxRanks];       // every rank's flag table (own entry: local address)
+    long long *stage_in[kExMaxRanks];   // every rank's staging buffer of this call's parity
+    long long *stage_out[kExMaxRanks];  // every rank's totals buffer of this call's parity
+    unsigned *status;                   // own status word
+    unsigned long long timeout_ns;
+};
+cudaError_t launch_exchange_allreduce(const ExchangeLaunch &x, cudaStream_t stream);
+
 cudaError_t launch_fixed_to_float(const long long *hist, float *out, long long n, float scale, cudaStream_t s);
 cudaError_t launch_float_to_fixed(const float *in, long long *hist, long long n, cudaStream_t s);
 

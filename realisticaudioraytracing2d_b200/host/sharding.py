@@ -6,6 +6,10 @@ are independent -- the RNG is a pure function of the global ray id and the frame
 its private Q23.40 histogram, and a single all-reduce(sum, int64) of bins x bands words produces the
 complete histogram on every rank.  Integer addition commutes, so the result is bit-identical for any W.
 Batched listeners / streams shard by contiguous batch range with no collective at all.
+
+Two interchangeable data paths for that all-reduce: `PeerExchange` -- the library's own kernel over
+CUDA-IPC-mapped peer memory (rar_exchange_*; the process group only carries the 80-byte handles at set-up
+and the tear-down barrier) -- and `allreduce_histogram`, ncclAllReduce on a zero-copy view of the slot.
 """
 from __future__ import annotations
 
@@ -45,3 +49,48 @@ class DeviceHistogram:
         ptr, n = ctx.ir_device_ptr(slot)
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         self.tensor = torch.as_tensor(self, device=device)
+
+
+def gather_handles(handle: bytes, group=None):
+    """All ranks' exchange handles in rank order (the only use of the process group on the exchange path)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, bytes(handle), group=group)
+    if any(not isinstance(h, (bytes, bytearray)) or len(h) != len(handle) for h in out):
+        raise RuntimeError("a rank delivered a malformed exchange handle")
+    return [bytes(h) for h in out]
+
+
+class PeerExchange:
+    """The all-reduce of the ray-range sharding as one kernel per rank over NVLink peer memory.
+
+    Collective construction: every rank of `group` must create it with the same capacity.  `allreduce(slot)`
+    only enqueues on the context's stream; `close()` is collective too (it fences the peers before unmapping).
+    """
+
+    def __init__(self, ctx, capacity_words: int, group=None):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group (one process per GPU)")
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handles = gather_handles(ctx.exchange_create(capacity_words), group)
+        ctx.exchange_connect(self.rank, self.world, handles)
+        dist.barrier(group=group)   # nobody signals a peer that has not mapped the regions yet
+        self._open = True
+
+    def allreduce(self, slot: int, mode: int = 0) -> None:
+        self.ctx.exchange_allreduce(slot, mode)
+
+    def check(self) -> None:
+        """Blocking: raises if a peer failed to reach a barrier of an earlier call."""
+        self.ctx.exchange_status()
+
+    def close(self) -> None:
+        import torch.distributed as dist
+        if self._open:
+            self._open = False
+            self.ctx.sync()
+            dist.barrier(group=self.group)
+            self.ctx.exchange_destroy()

@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from realisticaudioraytracing2d_b200 import scenes
-from realisticaudioraytracing2d_b200.host.sharding import allreduce_histogram, dispatched_threads, shard_range
+from realisticaudioraytracing2d_b200.host.sharding import (allreduce_histogram, dispatched_threads, gather_handles,
+                                                           shard_range)
 from tests.common import oracle_params, oracle_walls, trace_kwargs
 
 
@@ -26,6 +27,9 @@ def _worker(rank, world, port, out_dir):
     t = torch.from_numpy(part.copy())
     allreduce_histogram(t)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), t.numpy())
+    # the transport of the peer-memory exchange's handles: rank order, every rank sees all of them
+    handles = gather_handles(bytes([rank]) * 80)
+    assert handles == [bytes([r]) * 80 for r in range(world)]
     dist.destroy_process_group()
 
 
