@@ -64,6 +64,10 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_ir_device_ptr(IntPtr ctx, int slot, out IntPtr devicePtr, out long nWords);
 
         [DllImport(Lib)] public static extern int rar_allreduce_slots([In] IntPtr[] contexts, int n, int slot);
+        // LoadSample (RayTraceManager.cs:135-167) for a batch of clips on the GPU
+        [DllImport(Lib)] public static extern long rar_prepared_length(long samples, int clipFrequency, int sampleRate);
+        [DllImport(Lib)] public static extern int rar_prepare_clips(IntPtr ctx, [In] float[] raw, long samples, int channels, int clipFrequency, int sampleRate, int nClips, [Out] float[] output, long outStride);
+        [DllImport(Lib)] public static extern int rar_prepare_clips_device(IntPtr ctx, IntPtr dRaw, long samples, int channels, int clipFrequency, int sampleRate, int nClips, IntPtr dOut, long outStride);
         // one process per GPU: all-reduce kernel over CUDA-IPC peer memory (handles are 80 bytes each)
         [DllImport(Lib)] public static extern int rar_exchange_create(IntPtr ctx, long capacityWords, [Out] byte[] handle);
         [DllImport(Lib)] public static extern int rar_exchange_connect(IntPtr ctx, int rank, int world, [In] byte[] handles);

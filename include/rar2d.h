@@ -219,6 +219,25 @@ RAR_API int rar_exchange_allreduce(rar_context *ctx, int32_t slot, int32_t mode)
 RAR_API int rar_exchange_status(rar_context *ctx);
 RAR_API int rar_exchange_destroy(rar_context *ctx);
 
+/* ---- clip preparation -------------------------------------------------------------- */
+
+/* RayTraceManager.cs:135-167 LoadSample for a batch of n_clips equally shaped clips: mono mix (channels summed in
+ * order, divided by the channel count, :141-147) and, when clip_frequency != sample_rate, the reference's linear
+ * resampling (:150-163): ratio = (float)clip_frequency / sample_rate, newLength = RoundToInt(samples / ratio)
+ * (half to even), out[i] = Lerp(mono[floor(i*ratio)], mono[min(floor(i*ratio)+1, samples-1)], frac).  Plain IEEE
+ * binary32 without contraction, as the C# computes it: results are bit-exact.
+ *   raw  [n_clips][samples][channels] interleaved, as AudioClip.GetData returns it;
+ *   out  [n_clips][out_stride]; rar_prepared_length(...) values are written per clip (out_stride >= that).
+ * rar_prepare_clips takes host arrays and blocks; rar_prepare_clips_device takes device addresses, enqueues on
+ * the context's stream and returns. */
+RAR_API int64_t rar_prepared_length(int64_t samples, int32_t clip_frequency, int32_t sample_rate);
+RAR_API int rar_prepare_clips(rar_context *ctx, const float *raw, int64_t samples, int32_t channels,
+                              int32_t clip_frequency, int32_t sample_rate, int32_t n_clips, float *out,
+                              int64_t out_stride);
+RAR_API int rar_prepare_clips_device(rar_context *ctx, const void *d_raw, int64_t samples, int32_t channels,
+                                     int32_t clip_frequency, int32_t sample_rate, int32_t n_clips, void *d_out,
+                                     int64_t out_stride);
+
 /* ---- ray tracing ------------------------------------------------------------------------------ */
 
 /* RayTraceManager.cs:179-210 RunSimulation (Trace dispatch :205) fused with :220-232

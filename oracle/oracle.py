@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
         L.orc_convolve.argtypes = [C.c_void_p, i32, C.c_void_p, i32, i32, C.c_void_p, C.c_int]
         L.orc_convolve_f64.restype = None
         L.orc_convolve_f64.argtypes = [C.c_void_p, i32, C.c_void_p, i32, i32, C.c_void_p, C.c_int]
+        L.orc_load_sample.restype = i64
+        L.orc_load_sample.argtypes = [C.c_void_p, i64, i32, i32, i32, C.c_void_p]
         L.orc_add_loop.restype = C.c_int
         L.orc_add_loop.argtypes = [C.c_void_p, C.c_int] + [f32] * 10 + [C.c_void_p]
         L.orc_num_threads.restype = C.c_int
@@ -189,6 +191,17 @@ def add_loop(local_xy, pos, qz, qw, scale, mat) -> np.ndarray:
     out = np.zeros(len(pts), dtype=SEGMENT_DTYPE)
     lib().orc_add_loop(pts.ctypes.data, len(pts), pos[0], pos[1], qz, qw, scale[0], scale[1],
                        mat[0], mat[1], mat[2], mat[3], out.ctypes.data)
+    return out
+
+
+def load_sample(raw, samples: int, channels: int, clip_frequency: int, sample_rate: int) -> np.ndarray:
+    """RayTraceManager.cs:135-167 LoadSample of one interleaved clip."""
+    a = np.ascontiguousarray(raw, dtype=np.float32)
+    assert a.size >= samples * channels
+    n = lib().orc_load_sample(a.ctypes.data, samples, channels, clip_frequency, sample_rate, None)
+    out = np.zeros(n, dtype=np.float32)
+    if n:
+        lib().orc_load_sample(a.ctypes.data, samples, channels, clip_frequency, sample_rate, out.ctypes.data)
     return out
 
 

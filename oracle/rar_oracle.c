@@ -499,6 +499,40 @@ ORC_API int orc_add_loop(const float *local_xy, int n_points, float pos_x, float
     return n_points;
 }
 
+/* ---- RayTraceManager.cs:135-167 LoadSample -------------------------------------------------------
+ * C# on the CPU: IEEE binary32, no contraction.  Mathf.RoundToInt rounds half to even; Mathf.Lerp clamps t to
+ * [0,1].  Returns the prepared length; writes it to `out` when out != NULL. */
+ORC_API int64_t orc_load_sample(const float *raw, int64_t samples, int32_t channels, int32_t clip_frequency,
+                                int32_t sample_rate, float *out) {
+    if (samples <= 0) return 0;
+    float ratio = (float)clip_frequency / (float)sample_rate;                 /* :152 */
+    int resample = clip_frequency != sample_rate;                            /* :150 */
+    volatile float q = (float)samples / ratio;                               /* :153 */
+    int64_t new_len = resample ? (int64_t)nearbyintf(q) : samples;
+    if (!out) return new_len;
+    float *mono = (float *)malloc((size_t)samples * sizeof(float));
+    for (int64_t i = 0; i < samples; i++) {                                  /* :141-147 */
+        float sum = 0.0f;
+        for (int c = 0; c < channels; c++) sum += raw[i * channels + c];
+        mono[i] = sum / (float)channels;
+    }
+    if (!resample) {
+        memcpy(out, mono, (size_t)samples * sizeof(float));
+    } else {
+        for (int64_t i = 0; i < new_len; i++) {                              /* :156-163 */
+            float src = (float)(int32_t)i * ratio;
+            int64_t idx0 = (int64_t)floorf(src);
+            if (idx0 > samples - 1) idx0 = samples - 1; /* the C# would throw here; unreachable for sane ratios */
+            int64_t idx1 = idx0 + 1 < samples - 1 ? idx0 + 1 : samples - 1;
+            float t = src - (float)idx0;
+            t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+            out[i] = mono[idx0] + (mono[idx1] - mono[idx0]) * t;
+        }
+    }
+    free(mono);
+    return new_len;
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

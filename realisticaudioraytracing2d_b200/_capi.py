@@ -74,6 +74,9 @@ SYMBOLS = {
     "rar_exchange_allreduce": (C.c_int, [_p, _i32, _i32]),
     "rar_exchange_status": (C.c_int, [_p]),
     "rar_exchange_destroy": (C.c_int, [_p]),
+    "rar_prepared_length": (_i64, [_i64, _i32, _i32]),
+    "rar_prepare_clips": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64]),
+    "rar_prepare_clips_device": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64]),
     "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
     "rar_trace_frames": (C.c_int, [_p, C.POINTER(TraceParams), _i32, _i32]),
     "rar_trace_listeners": (C.c_int, [_p, C.POINTER(TraceParams), _p, _i32, _i32]),
@@ -245,6 +248,24 @@ class Context:
     def exchange_destroy(self) -> None:
         self._ck(self._lib.rar_exchange_destroy(self._h))
 
+    # clip preparation ---------------------------------------------------------------------------
+    def prepare_clips(self, raw: np.ndarray, samples: int, channels: int, clip_frequency: int, sample_rate: int,
+                      n_clips: int = 1) -> np.ndarray:
+        """rar_prepare_clips: LoadSample of n_clips interleaved clips [n_clips][samples][channels] -> [n_clips][newLength]."""
+        a = np.ascontiguousarray(raw, dtype=np.float32)
+        if a.size != n_clips * samples * channels:
+            raise ValueError("raw must hold n_clips * samples * channels values")
+        n = prepared_length(samples, clip_frequency, sample_rate)
+        out = np.zeros((n_clips, n), dtype=np.float32)
+        self._ck(self._lib.rar_prepare_clips(self._h, a.ctypes.data if a.size else None, samples, channels, clip_frequency,
+                                             sample_rate, n_clips, out.ctypes.data if out.size else None, n))
+        return out
+
+    def prepare_clips_device(self, d_raw: int, samples: int, channels: int, clip_frequency: int, sample_rate: int,
+                             n_clips: int, d_out: int, out_stride: int) -> None:
+        self._ck(self._lib.rar_prepare_clips_device(self._h, _p(d_raw), samples, channels, clip_frequency, sample_rate,
+                                                    n_clips, _p(d_out), out_stride))
+
     # trace ------------------------------------------------------------------------------------
     def trace(self, params: TraceParams, slot: int) -> None:
         self._ck(self._lib.rar_trace(self._h, C.byref(params), slot))
@@ -309,6 +330,11 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.rar_launch_count(self._h))
+
+
+def prepared_length(samples: int, clip_frequency: int, sample_rate: int) -> int:
+    """rar_prepared_length: the length LoadSample produces (RayTraceManager.cs:150-153); host-only, needs no device."""
+    return int(load().rar_prepared_length(samples, clip_frequency, sample_rate))
 
 
 def allreduce_slots(contexts, slot: int) -> None:

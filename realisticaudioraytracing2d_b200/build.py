@@ -25,6 +25,7 @@ UNITS = [
     ("trace_kernel.cu", ["--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
     ("conv_kernels.cu", []),
     ("exchange_kernel.cu", []),
+    ("clip_kernel.cu", ["--fmad=false", "-prec-div=true", "-ftz=false"]),
     ("rar2d_api.cu", []),
 ]
 HEADERS = ["rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_layout.h", "rar_internal.h", "../../include/rar2d.h"]

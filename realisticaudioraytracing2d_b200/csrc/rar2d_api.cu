@@ -3,6 +3,7 @@
 // There is no CPU path here: every compute entry point needs a CUDA device and fails otherwise.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -138,6 +139,7 @@ struct rar_context {
     DevBuf<f4> d_debug;
     int debug_entries = 0;
     DevBuf<float> d_irf;  // float view of a slot (scratch)
+    DevBuf<float> d_clip_raw, d_clip_out;  // rar_prepare_clips staging
     DevBuf<f2> d_listeners;                        // batched-listener launch arguments
     DevBuf<unsigned long long *> d_listener_hists;
     std::vector<Ticket *> tickets;
@@ -371,6 +373,8 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_counters.release();
     ctx->d_debug.release();
     ctx->d_irf.release();
+    ctx->d_clip_raw.release();
+    ctx->d_clip_out.release();
     ctx->d_listeners.release();
     ctx->d_listener_hists.release();
     ctx->d_grid_start.release();
@@ -724,6 +728,73 @@ int rar_exchange_status(rar_context *ctx) {
     RAR_CUDA(ctx, cudaMemcpyAsync(&st, X.region + kExFlagWords * sizeof(unsigned), sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
     RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (st) return fail(ctx, RAR_ERR_STATE, "a peer did not reach the exchange barrier within the time limit");
+    return RAR_OK;
+}
+
+// ---- clip preparation -----------------------------------------------------------------------------------
+
+int64_t rar_prepared_length(int64_t samples, int32_t clip_frequency, int32_t sample_rate) {
+    if (samples <= 0 || clip_frequency <= 0 || sample_rate <= 0) return 0;
+    if (clip_frequency == sample_rate) return samples;
+    const float ratio = (float)clip_frequency / (float)sample_rate;  // RayTraceManager.cs:152
+    volatile float q = (float)samples / ratio;                       // :153, rounded to binary32 before RoundToInt
+    return (int64_t)std::nearbyintf(q);                              // Mathf.RoundToInt: half to even
+}
+
+static int prepare_clips_common(rar_context *ctx, const float *d_raw, int64_t samples, int32_t channels, int32_t clip_frequency,
+                                int32_t sample_rate, int32_t n_clips, float *d_out, int64_t out_stride) {
+    ClipPrep a;
+    a.raw = d_raw;
+    a.out = d_out;
+    a.samples = samples;
+    a.new_len = rar_prepared_length(samples, clip_frequency, sample_rate);
+    a.out_stride = out_stride;
+    a.channels = channels;
+    a.n_clips = n_clips;
+    a.resample = clip_frequency != sample_rate;
+    a.ratio = (float)clip_frequency / (float)sample_rate;
+    RAR_CUDA(ctx, launch_prepare_clips(a, ctx->stream, ctx->dev.sm_count));
+    if (a.n_clips > 0 && a.new_len > 0) ctx->launches++;
+    return RAR_OK;
+}
+
+static int check_clip_args(rar_context *ctx, const void *raw, int64_t samples, int32_t channels, int32_t clip_frequency,
+                           int32_t sample_rate, int32_t n_clips, const void *out, int64_t out_stride) {
+    if (samples < 0 || n_clips < 0 || channels < 1 || clip_frequency <= 0 || sample_rate <= 0)
+        return fail(ctx, RAR_ERR_INVALID, "bad clip shape");
+    if (samples > 0x7fffffffLL) return fail(ctx, RAR_ERR_UNSUPPORTED, "clips are limited to 2^31-1 samples (AudioClip.samples is an int)");
+    const int64_t n = rar_prepared_length(samples, clip_frequency, sample_rate);
+    if (n > 0x7fffffffLL) return fail(ctx, RAR_ERR_UNSUPPORTED, "the prepared length exceeds 2^31-1 samples (newLength is an int)");
+    if (out_stride < n) return fail(ctx, RAR_ERR_INVALID, "out_stride is smaller than the prepared length");
+    if (n_clips > 0 && ((samples > 0 && !raw) || (n > 0 && !out))) return fail(ctx, RAR_ERR_INVALID, "null clip array");
+    return RAR_OK;
+}
+
+int rar_prepare_clips_device(rar_context *ctx, const void *d_raw, int64_t samples, int32_t channels, int32_t clip_frequency,
+                             int32_t sample_rate, int32_t n_clips, void *d_out, int64_t out_stride) {
+    RAR_ENTER(ctx);
+    int rc = check_clip_args(ctx, d_raw, samples, channels, clip_frequency, sample_rate, n_clips, d_out, out_stride);
+    if (rc != RAR_OK) return rc;
+    return prepare_clips_common(ctx, static_cast<const float *>(d_raw), samples, channels, clip_frequency, sample_rate, n_clips,
+                                static_cast<float *>(d_out), out_stride);
+}
+
+int rar_prepare_clips(rar_context *ctx, const float *raw, int64_t samples, int32_t channels, int32_t clip_frequency,
+                      int32_t sample_rate, int32_t n_clips, float *out, int64_t out_stride) {
+    RAR_ENTER(ctx);
+    int rc = check_clip_args(ctx, raw, samples, channels, clip_frequency, sample_rate, n_clips, out, out_stride);
+    if (rc != RAR_OK) return rc;
+    const int64_t n = rar_prepared_length(samples, clip_frequency, sample_rate);
+    if (n_clips == 0 || n == 0) return RAR_OK;
+    const size_t in_words = (size_t)n_clips * samples * channels, out_words = (size_t)n_clips * n;
+    RAR_CUDA(ctx, ctx->d_clip_raw.reserve(in_words + 4));
+    RAR_CUDA(ctx, ctx->d_clip_out.reserve(out_words));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_clip_raw.p, raw, in_words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = prepare_clips_common(ctx, ctx->d_clip_raw.p, samples, channels, clip_frequency, sample_rate, n_clips, ctx->d_clip_out.p, n);
+    if (rc != RAR_OK) return rc;
+    RAR_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_stride * sizeof(float), ctx->d_clip_out.p, (size_t)n * sizeof(float),
+                                    (size_t)n * sizeof(float), (size_t)n_clips, cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RAR_OK;
 }
 

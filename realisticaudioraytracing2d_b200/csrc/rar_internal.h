@@ -113,6 +113,18 @@ struct StreamConv {
 };
 cudaError_t launch_stream_step(const StreamConv &c, const float *d_in, float *d_out, cudaStream_t s, int *launches);
 
+// clip_kernel.cu -- LoadSample (mono mix + linear resample) for a batch of equally shaped clips
+struct ClipPrep {
+    const float *raw;      // [n_clips][samples][channels]
+    float *out;            // [n_clips][out_stride], new_len valid values per clip
+    long long samples, new_len, out_stride;
+    int channels, n_clips;
+    int resample;          // 0: clip frequency == sample rate (mono mix only)
+    float ratio;           // (float)clip_frequency / sample_rate
+    int tile;              // outputs per block tile (set by the launcher)
+};
+cudaError_t launch_prepare_clips(const ClipPrep &a, cudaStream_t s, int sm_count);
+
 void conv_init_tables();  // uploads twiddle tables to constant memory of the current device (idempotent per device)
 
 }  // namespace rar

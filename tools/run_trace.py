@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs the trace kernel (or the streaming convolver) a few times; the short command line that ncu wraps.
 
-    python tools/run_trace.py c2|maze|maze8|conv [reps]
+    python tools/run_trace.py c2|c1|maze|maze8|wallsN|conv|clip [reps]
 """
 import os
 import sys
@@ -28,6 +28,19 @@ def main():
             t0 = time.perf_counter()
             cv.process(x)
             print(f"conv block {1e3 * (time.perf_counter() - t0):.3f} ms (host copies included)")
+        return
+    if what == "clip":                      # bench.py's clip_prep leg: 256 stereo 10 s clips, 44.1 -> 48 kHz
+        import torch
+        n_clips, samples, ch, freq, rate = 256, 441000, 2, 44100, 48000
+        n_out = _capi.prepared_length(samples, freq, rate)
+        raw = torch.rand((n_clips, samples, ch), device="cuda") * 2 - 1
+        out = torch.empty((n_clips, n_out), device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ctx.prepare_clips_device(raw.data_ptr(), samples, ch, freq, rate, n_clips, out.data_ptr(), n_out)
+            ctx.sync()
+            print(f"clip prep {1e3 * (time.perf_counter() - t0):.3f} ms")
         return
     if what == "c2":
         sc, bands = scenes.shoebox(), 1
