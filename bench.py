@@ -525,7 +525,7 @@ def bench_clip_prep(ctx, _capi, torch, stream, dev, peaks, peaks_kind):
     ach = nbytes / (ms * 1e-3) / 1e9
     res = {"workload": f"{n_clips} stereo clips x {samples} samples @ {freq} Hz -> mono {n_out} samples @ {rate} Hz, resident in HBM",
            "ms": ms, "output_samples_per_s": n_clips * n_out / (ms * 1e-3),
-           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("prepare_clips_kernel"),
                         "kernel": "prepare_clips_kernel", "peak_kind": peaks_kind, "algorithmic_bytes_per_launch": nbytes}}
     del raw, out
     return res
