@@ -170,6 +170,21 @@ class RayTraceManager:
         a, b = mono[idx0], mono[idx1]
         return (a + (b - a) * t).astype(np.float32)                      # Mathf.Lerp
 
+    def LoadSamples(self, clips) -> list:
+        """LoadSample for many sources at once on the GPU (rar_prepare_clips): clips of the same shape
+        (samples, channels, frequency) are prepared by one launch per shape group; results are bit-identical
+        to LoadSample and come back in the order given."""
+        out = [None] * len(clips)
+        groups = {}
+        for i, c in enumerate(clips):
+            groups.setdefault((c.samples, c.channels, c.frequency), []).append(i)
+        for (samples, ch, freq), idx in groups.items():
+            raw = np.concatenate([np.asarray(clips[i].GetData(), dtype=np.float32)[: samples * ch] for i in idx])
+            res = self._ctx.prepare_clips(raw, samples, ch, freq, self.sampleRate, len(idx))
+            for k, i in enumerate(idx):
+                out[i] = res[k]
+        return out
+
     def _ir_length(self) -> int:
         return int(np.float32(self.sampleRate) * np.float32(self.reverbDuration))   # (int)(sampleRate * reverbDuration)
 

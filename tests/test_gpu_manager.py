@@ -102,3 +102,17 @@ def test_bake_audio_whole_clip(ctx, oracle):
     want = want / np.abs(want).max()
     assert out.shape == (len(clip) + 72000,) and abs(np.abs(out).max() - 1.0) < 1e-6     # PlayResult peak-normalises
     assert rel_l2(out, want) <= 1e-4
+
+
+def test_load_samples_batched_equals_load_sample(ctx):
+    """RayTraceManager.LoadSamples (GPU, rar_prepare_clips) == LoadSample (the C#'s CPU arithmetic), clip by clip."""
+    m = RayTraceManager(context=ctx)
+    m.sampleRate = 48000
+    rng = np.random.default_rng(5)
+    clips = [AudioClip(rng.uniform(-1, 1, 4410 * 2).astype(np.float32), 2, 44100),
+             AudioClip(rng.uniform(-1, 1, 3000).astype(np.float32), 1, 48000),
+             AudioClip(rng.uniform(-1, 1, 4410 * 2).astype(np.float32), 2, 44100),
+             AudioClip(rng.uniform(-1, 1, 2205 * 3).astype(np.float32), 3, 22050)]
+    got = m.LoadSamples(clips)
+    for c, g in zip(clips, got):
+        assert np.array_equal(g, m.LoadSample(c))
