@@ -125,8 +125,8 @@ struct rar_context {
     DevBuf<float> d_band_abs;
     int n_walls = -1;  // -1: never set
     int band_rows = 0, band_count = 0;
-    std::vector<f4> h_geo, h_mat0;
-    std::vector<f2> h_mat1;
+    PinnedBuf<f4> h_planes;            // pinned staging of the geo | mat0 | mat1 planes of one upload
+    cudaEvent_t walls_uploaded = nullptr;  // the staging buffer may be rewritten once this has completed
     std::vector<rar_segment> h_walls;  // kept for the lazy grid build
     GridHost h_grid;
     DevBuf<uint32_t> d_grid_start, d_grid_items;
@@ -366,6 +366,8 @@ int rar_destroy(rar_context *ctx) {
         if (s.d_hist) cudaFree(s.d_hist);
         if (s.d_H) cudaFree(s.d_H);
     }
+    ctx->h_planes.release();
+    if (ctx->walls_uploaded) cudaEventDestroy(ctx->walls_uploaded);
     ctx->d_geo.release();
     ctx->d_mat0.release();
     ctx->d_mat1.release();
@@ -407,19 +409,25 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
     if (n < 0 || (n > 0 && !segments)) return fail(ctx, RAR_ERR_INVALID, "bad wall array");
     static_assert(sizeof(rar_segment) == 40, "Segment must be 40 bytes (Helpers/SceneHelper.cs:15-22)");
     static_assert(sizeof(rar_ray_info) == 16, "RayInfo must be 16 bytes (RayTraceManager.cs:43)");
-    const size_t pad = (size_t)n + 2;  // mat1 plane is bulk-copied in 16-byte units
-    ctx->h_geo.assign(pad, f4{0, 0, 0, 0});
-    ctx->h_mat0.assign(pad, f4{0, 0, 0, 0});
-    ctx->h_mat1.assign(pad, f2{0, 0});
-    split_walls(segments, n, ctx->h_geo.data(), ctx->h_mat0.data(), ctx->h_mat1.data());
+    const size_t pad = ((size_t)n + 2 + 1) & ~(size_t)1;  // mat1 plane is bulk-copied in 16-byte units; even => planes stay 16-byte aligned
+    // Pinned staging: the three planes go up as asynchronous copies and the call returns without waiting for
+    // them; the next upload waits (normally not at all) for this one before it rewrites the staging buffer.
+    if (ctx->walls_uploaded) RAR_CUDA(ctx, cudaEventSynchronize(ctx->walls_uploaded));
+    else RAR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->walls_uploaded, cudaEventDisableTiming));
+    if (pad * 3 > ctx->h_planes.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // reallocation frees the old buffer
+    RAR_CUDA(ctx, ctx->h_planes.reserve(pad * 3));
+    f4 *h_geo = ctx->h_planes.p, *h_mat0 = h_geo + pad;
+    f2 *h_mat1 = reinterpret_cast<f2 *>(h_mat0 + pad);
+    std::memset(h_geo, 0, pad * (2 * sizeof(f4) + sizeof(f2)));
+    split_walls(segments, n, h_geo, h_mat0, h_mat1);
     RAR_CUDA(ctx, ctx->d_geo.reserve(pad));
     RAR_CUDA(ctx, ctx->d_mat0.reserve(pad));
     RAR_CUDA(ctx, ctx->d_mat1.reserve(pad));
-    // The previous planes may still be read by an enqueued trace; stream order makes the copy safe.
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_geo.p, ctx->h_geo.data(), pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat0.p, ctx->h_mat0.data(), pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat1.p, ctx->h_mat1.data(), pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors are pageable: finish before returning
+    // The previous planes may still be read by an enqueued trace; stream order makes the copies safe.
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_geo.p, h_geo, pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat0.p, h_mat0, pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat1.p, h_mat1, pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaEventRecord(ctx->walls_uploaded, ctx->stream));
     if (n != ctx->n_walls) {
         ctx->band_rows = 0;
         ctx->band_count = 0;
