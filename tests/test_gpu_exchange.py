@@ -47,6 +47,11 @@ def test_exchange_state_machine_on_one_rank(ctx):
     ctx.exchange_destroy()                                      # idempotent
 
 
+def _odd_payload(rank, words):
+    """Small integers times 2^-10: exactly representable, so the quantised words are known on the host."""
+    return (np.random.default_rng(100 + rank).integers(-1000, 1000, words) / 1024.0).astype(np.float32)
+
+
 def _worker(rank, world, port, out_dir, bands):
     import torch
     import torch.distributed as dist
@@ -70,8 +75,16 @@ def _worker(rank, world, port, out_dir, bands):
             ctx.ir_clear(it, n, bands)
             ctx.trace(capi_params(_capi, dict(kw, ray_begin=lo, ray_end=hi, rng_state_offset=1 + it % 2)), it)
             ex.allreduce(it, mode)
+        # an odd word count (the last 16-byte vector is half padding) and a single word, in both modes
+        odd = []
+        for k, (words, mode) in enumerate([(4801, _capi.RAR_EXCHANGE_ONE_SHOT), (4801, _capi.RAR_EXCHANGE_TWO_SHOT),
+                                           (1, _capi.RAR_EXCHANGE_ONE_SHOT), (1, _capi.RAR_EXCHANGE_TWO_SHOT)]):
+            ctx.ir_write(10 + k, _odd_payload(rank, words))
+            ex.allreduce(10 + k, mode)
+            odd.append(ctx.ir_read_fixed(10 + k, words))
         ex.check()
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.stack([ctx.ir_read_fixed(it, n * bands) for it in range(5)]))
+        np.save(os.path.join(out_dir, f"odd{rank}.npy"), np.concatenate(odd))
         ex.close()
     finally:
         ctx.destroy()
@@ -93,7 +106,10 @@ def test_peer_exchange_matches_unsharded_trace(tmp_path, oracle, bands):
     want = [oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, rng_state_offset=f)),
                          band_abs=sc.band_absorption if bands > 1 else None).hist for f in (1, 2)]
     assert want[0].any() and not np.array_equal(want[0], want[1])
+    odd_want = np.concatenate([sum((_odd_payload(r, words).astype(np.float64) * 2.0 ** 40).astype(np.int64) for r in range(world))
+                               for words in (4801, 4801, 1, 1)])
     for r in range(world):
         got = np.load(tmp_path / f"rank{r}.npy")
         for it in range(5):
             assert np.array_equal(got[it], want[it % 2]), (r, it)
+        assert np.array_equal(np.load(tmp_path / f"odd{r}.npy"), odd_want), r
