@@ -284,22 +284,37 @@ def run_ours(args):
         exchange_compare = [peer_ms, nccl_ms, float(same)]
 
     # ---- end-to-end through the C-ABI with host buffers --------------------------------------------
-    ir_host = torch.empty(n_bins, dtype=torch.float32).pin_memory()   # the caller's (pinned) result buffer
+    # Every step uploads the scene from host memory and reads the finished IR back into the caller's host buffer.
+    # Steps alternate between the ping and pong slots (RayTraceManager.cs:36) and the readback is asynchronous
+    # (rar_ir_read_begin/_end, the analogue of AsyncGPUReadback), so step k+1's upload and trace are enqueued
+    # while step k's result is still on its way; every step's result is collected inside the timed region.
+    ir_host = [torch.empty(n_bins, dtype=torch.float32).pin_memory() for _ in range(2)]   # the caller's result buffers
     walls_host = np.ascontiguousarray(sc.walls)
+    ctx.ir_clear(1, n_bins, 1)
+    hist_ts = [hist_t, sharding.DeviceHistogram(ctx, 1, dev).tensor]
 
-    def e2e_step(frame):
-        ctx.set_walls(walls_host)                      # H2D: 40 B per wall
-        ctx.ir_clear(0, n_bins, 1)
-        ctx.trace(params(frame), 0)
-        exchange()
-        ctx.ir_read_into(0, ir_host.data_ptr(), n_bins)   # D2H: the float IR
+    def e2e_run(fr):
+        pending = None
+        for k, frame in enumerate(fr):
+            s = k & 1
+            ctx.set_walls(walls_host)                      # H2D: 40 B per wall
+            ctx.ir_clear(s, n_bins, 1)
+            ctx.trace(params(frame), s)
+            if world > 1:
+                if use_nccl:
+                    sharding.allreduce_histogram(hist_ts[s])
+                else:
+                    ex.allreduce(s)
+            t = ctx.ir_read_begin(s, n_bins)               # D2H: the float IR
+            if pending is not None:
+                ctx.ir_read_end(pending[0], n_bins, ir_host[pending[1]].data_ptr())
+            pending = (t, s)
+        ctx.ir_read_end(pending[0], n_bins, ir_host[pending[1]].data_ptr())
 
-    for w in range(min(args.warmup, 3)):
-        e2e_step(2000 + w)
+    e2e_run([2000 + w for w in range(max(2, min(args.warmup, 3)))])
     barrier()
     t0 = time.perf_counter()
-    for f in frames:
-        e2e_step(f)
+    e2e_run(frames)
     barrier()
     e2e_s = time.perf_counter() - t0
 

@@ -63,6 +63,8 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_ir_write(IntPtr ctx, int slot, [In] float[] ir, int impulseLength, int bands);
         [DllImport(Lib)] public static extern int rar_ir_device_ptr(IntPtr ctx, int slot, out IntPtr devicePtr, out long nWords);
 
+        [DllImport(Lib)] public static extern int rar_ir_read_begin(IntPtr ctx, int slot, long n, out int ticket);
+        [DllImport(Lib)] public static extern int rar_ir_read_end(IntPtr ctx, int ticket, [Out] float[] output, long n);
         [DllImport(Lib)] public static extern int rar_allreduce_slots([In] IntPtr[] contexts, int n, int slot);
         // LoadSample (RayTraceManager.cs:135-167) for a batch of clips on the GPU
         [DllImport(Lib)] public static extern long rar_prepared_length(long samples, int clipFrequency, int sampleRate);

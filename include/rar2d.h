@@ -172,6 +172,14 @@ RAR_API int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length,
  * convolution, AudioConvolve.compute:30).  n = impulse_length*bands values.  Blocking. */
 RAR_API int rar_ir_read(rar_context *ctx, int32_t slot, float *out, int64_t n);
 
+/* The same read without blocking the caller, the analogue of AsyncGPUReadback.Request on the IR buffer
+ * (RayTraceManager.cs:114-121 does this for the convolution output): _begin enqueues the conversion and the copy
+ * into pinned memory behind the work already on the stream and returns a ticket; rar_poll(ticket) tells whether it
+ * has completed; _end waits if necessary, copies n values to `out` and releases the ticket.  Lets a host overlap
+ * the next frame's upload and trace with this frame's readback. */
+RAR_API int rar_ir_read_begin(rar_context *ctx, int32_t slot, int64_t n, int32_t *ticket);
+RAR_API int rar_ir_read_end(rar_context *ctx, int32_t ticket, float *out, int64_t n);
+
 /* The slot's exact contents, for bit-exact comparison.  Blocking. */
 RAR_API int rar_ir_read_fixed(rar_context *ctx, int32_t slot, int64_t *out, int64_t n);
 

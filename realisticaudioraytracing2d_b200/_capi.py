@@ -65,6 +65,8 @@ SYMBOLS = {
     "rar_set_wall_band_absorption": (C.c_int, [_p, _p, _i32, _i32]),
     "rar_ir_clear": (C.c_int, [_p, _i32, _i32, _i32]),
     "rar_ir_read": (C.c_int, [_p, _i32, _p, _i64]),
+    "rar_ir_read_begin": (C.c_int, [_p, _i32, _i64, C.POINTER(_i32)]),
+    "rar_ir_read_end": (C.c_int, [_p, _i32, _p, _i64]),
     "rar_ir_read_fixed": (C.c_int, [_p, _i32, _p, _i64]),
     "rar_ir_write": (C.c_int, [_p, _i32, _p, _i32, _i32]),
     "rar_ir_device_ptr": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64)]),
@@ -212,6 +214,21 @@ class Context:
     def ir_read_into(self, slot: int, host_ptr: int, n: int) -> None:
         """rar_ir_read into caller-owned host memory (e.g. a pinned buffer), n floats."""
         self._ck(self._lib.rar_ir_read(self._h, slot, _p(host_ptr), n))
+
+    def ir_read_begin(self, slot: int, n: int) -> int:
+        """rar_ir_read_begin: enqueue the readback of n floats, returns a ticket (poll() / ir_read_end())."""
+        t = _i32(-1)
+        self._ck(self._lib.rar_ir_read_begin(self._h, slot, n, C.byref(t)))
+        return t.value
+
+    def ir_read_end(self, ticket: int, n: int, host_ptr: int = 0) -> np.ndarray:
+        """rar_ir_read_end into a new array, or into caller-owned memory when host_ptr is given."""
+        if host_ptr:
+            self._ck(self._lib.rar_ir_read_end(self._h, ticket, _p(host_ptr), n))
+            return None
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self._lib.rar_ir_read_end(self._h, ticket, out.ctypes.data, n))
+        return out
 
     def ir_read_fixed(self, slot: int, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.int64)

@@ -280,6 +280,20 @@ void free_ticket(Ticket *t) {
     delete t;
 }
 
+// An inactive ticket of the context (or a new one); negative status on failure.
+int acquire_ticket(rar_context *ctx) {
+    for (size_t i = 0; i < ctx->tickets.size(); i++)
+        if (!ctx->tickets[i]->active) return (int)i;
+    Ticket *t = new (std::nothrow) Ticket();
+    if (!t) return fail(ctx, RAR_ERR_NOMEM, "out of host memory");
+    if (cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming) != cudaSuccess) {
+        delete t;
+        return fail(ctx, RAR_ERR_CUDA, "cudaEventCreate failed");
+    }
+    ctx->tickets.push_back(t);
+    return (int)ctx->tickets.size() - 1;
+}
+
 // Makes the cached partition spectra of a slot current.
 int ensure_slot_spectra(rar_context *ctx, Slot &S) {
     const int n_part = (S.impulse_length + kBlock - 1) / kBlock;
@@ -508,6 +522,38 @@ int rar_ir_read(rar_context *ctx, int32_t slot, float *out, int64_t n) {
     RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n > have) std::memset(out + have, 0, (size_t)(n - have) * sizeof(float));
     return RAR_OK;
+}
+
+int rar_ir_read_begin(rar_context *ctx, int32_t slot, int64_t n, int32_t *ticket) {
+    RAR_ENTER(ctx);
+    if (!ticket) return fail(ctx, RAR_ERR_INVALID, "null ticket");
+    *ticket = -1;
+    if (n < 0 || n > 0x7fffffffLL) return fail(ctx, RAR_ERR_INVALID, "bad length");
+    Slot *S = get_slot(ctx, slot, false);
+    const long long words = (S && S->configured) ? (long long)S->impulse_length * S->bands : 0;
+    const long long have = n < words ? n : words;
+    const int id = acquire_ticket(ctx);
+    if (id < 0) return id;
+    Ticket &T = *ctx->tickets[id];
+    T.out_len = (int)n;
+    T.failed = false;
+    RAR_CUDA(ctx, T.h_out.reserve((size_t)n + 1));
+    RAR_CUDA(ctx, T.d_out.reserve((size_t)n + 1));
+    if (n > have) std::memset(T.h_out.p + have, 0, (size_t)(n - have) * sizeof(float));  // an unconfigured slot reads as zeros
+    if (have > 0) {
+        RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, T.d_out.p, have, 1.0f, ctx->stream));
+        ctx->launches++;
+        RAR_CUDA(ctx, cudaMemcpyAsync(T.h_out.p, T.d_out.p, (size_t)have * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RAR_CUDA(ctx, cudaEventRecord(T.done, ctx->stream));
+    T.active = true;
+    *ticket = id;
+    return RAR_OK;
+}
+
+int rar_ir_read_end(rar_context *ctx, int32_t ticket, float *out, int64_t n) {
+    if (n < 0 || n > 0x7fffffffLL) return fail(ctx, RAR_ERR_INVALID, "bad length");
+    return rar_convolve_end(ctx, ticket, out, (int32_t)n);  // same ticket mechanics: wait, copy out, release
 }
 
 int rar_ir_write(rar_context *ctx, int32_t slot, const float *ir, int32_t impulse_length, int32_t bands) {
@@ -992,19 +1038,8 @@ int rar_convolve_begin(rar_context *ctx, int32_t slot, const float *in, int32_t 
     const int ir_len = S->impulse_length;
     const int out_len = in_len + ir_len;  // AudioConvolve.compute:15
 
-    int id = -1;
-    for (size_t i = 0; i < ctx->tickets.size(); i++)
-        if (!ctx->tickets[i]->active) { id = (int)i; break; }
-    if (id < 0) {
-        Ticket *t = new (std::nothrow) Ticket();
-        if (!t) return fail(ctx, RAR_ERR_NOMEM, "out of host memory");
-        if (cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming) != cudaSuccess) {
-            delete t;
-            return fail(ctx, RAR_ERR_CUDA, "cudaEventCreate failed");
-        }
-        ctx->tickets.push_back(t);
-        id = (int)ctx->tickets.size() - 1;
-    }
+    const int id = acquire_ticket(ctx);
+    if (id < 0) return id;
     Ticket &T = *ctx->tickets[id];
     T.out_len = out_len;
     T.failed = false;

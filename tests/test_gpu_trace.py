@@ -451,3 +451,27 @@ def test_production_kernels_for_opaque_scenes(ctx, oracle, case):
     want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, flags=0)),
                         band_abs=sc.band_absorption if bands > 1 else None).hist
     assert np.array_equal(ctx.ir_read_fixed(0, n * bands), want) and np.count_nonzero(want) > 500
+
+
+def test_asynchronous_ir_readback(ctx, oracle):
+    """rar_ir_read_begin/_end (AsyncGPUReadback analogue): same values as the blocking read, several in flight."""
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc, ray_count=2000)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    tickets = []
+    for s in (0, 1):
+        ctx.ir_clear(s, n, 1)
+        ctx.trace(capi_params(_capi, dict(kw, rng_state_offset=1 + s)), s)
+        tickets.append(ctx.ir_read_begin(s, n + 5))         # longer than the slot: zero tail
+    assert tickets[0] != tickets[1]
+    got = [ctx.ir_read_end(t, n + 5) for t in tickets]
+    for s in (0, 1):
+        assert np.array_equal(got[s][:n], ctx.ir_read(s, n)) and not got[s][n:].any() and got[s].any()
+    assert not np.array_equal(got[0], got[1])
+    t = ctx.ir_read_begin(77, 16)                           # never configured: reads as zeros
+    while not ctx.poll(t):
+        pass
+    assert not ctx.ir_read_end(t, 16).any()
+    with pytest.raises(_capi.RarError):
+        ctx.ir_read_end(t, 16)                              # the ticket was released
