@@ -197,7 +197,13 @@ def run_ours(args):
     # The all-reduce of the ray-range sharding: the library's own kernel over CUDA-IPC peer memory (the process
     # group only delivers the handles); RAR_BENCH_EXCHANGE=nccl selects ncclAllReduce on the same buffer instead.
     use_nccl = os.environ.get("RAR_BENCH_EXCHANGE", "peer") == "nccl"
-    ex = sharding.PeerExchange(ctx, n_bins) if world > 1 else None
+    ex = None
+    if world > 1 and not use_nccl:
+        try:
+            ex = sharding.PeerExchange(ctx, n_bins)
+        except RuntimeError as e:   # raised on every rank or on none: CUDA IPC is unavailable between these processes
+            sys.stderr.write(f"[bench] {e}; using ncclAllReduce for the exchange\n")
+            use_nccl = True
 
     def exchange(nccl=use_nccl):
         if world == 1:
@@ -262,7 +268,7 @@ def run_ours(args):
 
     # the same steps with the other all-reduce, for comparison (and a bit-for-bit check of the two)
     exchange_compare = None
-    if world > 1:
+    if world > 1 and ex is not None:
         ex.check()
         other = []
         for f in frames:
@@ -323,11 +329,12 @@ def run_ours(args):
     if world > 1:
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        cmp_t = torch.tensor([exchange_compare[0], exchange_compare[1], -exchange_compare[2]], dtype=torch.float64, device=dev)
-        dist.all_reduce(cmp_t, op=dist.ReduceOp.MAX)
-        exchange_compare = {"peer_kernel_ms_per_step": float(cmp_t[0]) / len(frames),
-                            "nccl_ms_per_step": float(cmp_t[1]) / len(frames),
-                            "bit_identical": bool(float(cmp_t[2]) == -1.0)}
+        if exchange_compare is not None:
+            cmp_t = torch.tensor([exchange_compare[0], exchange_compare[1], -exchange_compare[2]], dtype=torch.float64, device=dev)
+            dist.all_reduce(cmp_t, op=dist.ReduceOp.MAX)
+            exchange_compare = {"peer_kernel_ms_per_step": float(cmp_t[0]) / len(frames),
+                                "nccl_ms_per_step": float(cmp_t[1]) / len(frames),
+                                "bit_identical": bool(float(cmp_t[2]) == -1.0)}
         sm = tt.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms, tests_all, tests_exec_all = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
@@ -415,7 +422,8 @@ def run_ours(args):
         line.update(extra)
         _emit(line)
     if world > 1:
-        ex.close()
+        if ex is not None:
+            ex.close()
         dist.barrier()
         dist.destroy_process_group()
     ctx.destroy()

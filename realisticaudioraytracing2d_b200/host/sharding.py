@@ -75,9 +75,28 @@ class PeerExchange:
             raise RuntimeError("PeerExchange needs an initialised process group (one process per GPU)")
         self.ctx, self.group = ctx, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        handles = gather_handles(ctx.exchange_create(capacity_words), group)
-        ctx.exchange_connect(self.rank, self.world, handles)
-        dist.barrier(group=group)   # nobody signals a peer that has not mapped the regions yet
+        # Set-up is all-or-nothing across the group: every rank reports whether it could create and map the
+        # regions, and either all ranks end up connected or all raise (so a caller can fall back consistently).
+        err = None
+        try:
+            handle = ctx.exchange_create(capacity_words)
+        except Exception as ex:  # noqa: BLE001 - reported to the peers below
+            handle, err = b"\0" * 80, f"create: {ex}"
+        handles = gather_handles(handle, group)
+        if err is None:
+            try:
+                ctx.exchange_connect(self.rank, self.world, handles)
+            except Exception as ex:  # noqa: BLE001
+                err = f"connect: {ex}"
+        status = [None] * self.world
+        dist.all_gather_object(status, err, group=group)   # also the barrier: nobody signals an unmapped peer
+        if any(st is not None for st in status):
+            try:
+                ctx.exchange_destroy()
+            except Exception:  # noqa: BLE001
+                pass
+            raise RuntimeError("peer-memory exchange unavailable: " +
+                               "; ".join(f"rank {r}: {st}" for r, st in enumerate(status) if st is not None))
         self._open = True
 
     def allreduce(self, slot: int, mode: int = 0) -> None:
