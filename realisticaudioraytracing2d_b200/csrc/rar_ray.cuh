@@ -24,6 +24,8 @@
 // through a uniform grid that visits a superset of the walls a query could accept (GridView below).
 #pragma once
 
+#include <cmath>
+
 #include "rar_math.cuh"
 
 namespace rar {
@@ -115,6 +117,19 @@ RAR_HD WallTest wall_test(const f4 s, float ox, float oy, float dx, float ndy) {
 RAR_HD bool wall_pass(const WallTest &t, float bound_m) {
     const float r = bound_m * t.dotP;
     return (fabsf(rar_fma(2.0f, t.num2, -t.dotP)) <= fabsf(t.dotP)) & (fabsf(rar_fma(2.0f, t.num1, -r)) <= fabsf(r));
+}
+
+// The filter while no hit has been found yet (bound = inf).  With an infinite bound the second clause of
+// wall_pass accepts every wall, including those the ray's line crosses BEHIND the origin, which the literal
+// formula then rejects at the price of a division.  Until a bound exists the clause is replaced by the sign
+// test it degenerates from: t1 = num1/dotP >= eps > 0 needs num1 and dotP of the same sign.
+RAR_HD bool wall_pass_unbounded(const WallTest &t) {
+#ifdef __CUDA_ARCH__
+    const bool forward = (__float_as_int(t.num1) ^ __float_as_int(t.dotP)) >= 0;
+#else
+    const bool forward = std::signbit(t.num1) == std::signbit(t.dotP);
+#endif
+    return (fabsf(rar_fma(2.0f, t.num2, -t.dotP)) <= fabsf(t.dotP)) & forward;
 }
 
 // ---- optional uniform grid over the walls (RAR_FLAG_USE_GRID) -------------------------------------------
@@ -280,6 +295,21 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
             closest_m = d * kSlack;                                  \
             hit = (W);                                               \
         }                                                            \
+    }
+    if (Scene::kPeelFirstBatch && n >= 4) {  // first batch: no bound yet
+        const WallTest t0 = wall_test(sc.geo(0), ox, oy, dx, ndy);
+        const WallTest t1 = wall_test(sc.geo(1), ox, oy, dx, ndy);
+        const WallTest t2 = wall_test(sc.geo(2), ox, oy, dx, ndy);
+        const WallTest t3 = wall_test(sc.geo(3), ox, oy, dx, ndy);
+        const bool p0 = wall_pass_unbounded(t0), p1 = wall_pass_unbounded(t1);
+        const bool p2 = wall_pass_unbounded(t2), p3 = wall_pass_unbounded(t3);
+        if (p0 | p1 | p2 | p3) {
+            if (p0) RAR_NEAREST_EXACT(t0, 0)
+            if (p1) RAR_NEAREST_EXACT(t1, 1)
+            if (p2) RAR_NEAREST_EXACT(t2, 2)
+            if (p3) RAR_NEAREST_EXACT(t3, 3)
+        }
+        w = 4;
     }
     for (; w + 4 <= n; w += 4) {
         const WallTest t0 = wall_test(sc.geo(w), ox, oy, dx, ndy);

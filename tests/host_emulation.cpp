@@ -12,6 +12,7 @@ namespace {
 template <bool GRID>
 struct HostSceneT {
     static constexpr bool kGrid = GRID;
+    static constexpr bool kPeelFirstBatch = !GRID;  // exercise the small-scene filter of the nearest-hit scan
     rar::GridView gv;
     const rar::GridView &grid() const { return gv; }
     rar::f4 grid_geo(uint32_t i) const { return gv.item_geo[i]; }
