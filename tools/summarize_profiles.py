@@ -70,7 +70,7 @@ def main():
     lc = os.path.join(OUT, "launches_final.csv")
     if os.path.exists(lc):
         with open(os.path.join(PROF, f"{tag}_launches_summary.txt"), "w") as f:
-            f.write(launches(lc, "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 5 --warmup 3") + "\n")
+            f.write(launches(lc, "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1") + "\n")
         with open(lc) as src, open(os.path.join(PROF, f"{tag}_launches.csv"), "w") as dst:
             dst.write(src.read())
 
