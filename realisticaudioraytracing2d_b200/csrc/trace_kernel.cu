@@ -344,22 +344,38 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
             nee.has = 0;
             c.want_shadow = 0;
             c.shadow = ShadowRay{0.f, 0.f, 0.f, 0.f, 0.f};
-            bool hit_wall = false;
-            if (alive) {
-                hit_wall = bounce_begin<BANDS, COUNT>(sc, a.p, r, direct, c, &ctr, dbg ? dbg + i + 1 : nullptr, dbg_flags);
+            if constexpr (COOP || GRID) {
+                // the warp meets between the phases: for the cooperative shadow rays, and in grid mode because
+                // reconverging before the (long, divergent) cell walks measured 3 % faster than one merged region
+                bool hit_wall = false;
+                if (alive) {
+                    hit_wall = bounce_begin<BANDS, COUNT>(sc, a.p, r, direct, c, &ctr, dbg ? dbg + i + 1 : nullptr, dbg_flags);
+                }
+                const bool pending = hit_wall && c.want_shadow;
+                bool visible = true;
+                if (COOP) {
+                    __syncwarp();
+                    visible = coop_shadow<COUNT>(sc, pending, c.shadow, lane, ctr);
+                } else if (pending) {
+                    int tests = 0;
+                    visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
+                    if (COUNT) ctr.shadow_tests += (unsigned long long)tests;
+                }
+                if (alive) alive = hit_wall && bounce_finish<BANDS, COUNT, OPAQUE>(sc, a.p, r, nee, c, visible, &ctr);
+            } else if (alive) {
+                // per-thread shadow rays: the three phases of a live ray run inside one divergent region
+                alive = bounce_begin<BANDS, COUNT>(sc, a.p, r, direct, c, &ctr, dbg ? dbg + i + 1 : nullptr, dbg_flags);
+                if (alive) {
+                    bool visible = true;
+                    if (c.want_shadow) {
+                        int tests = 0;
+                        visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
+                        if (COUNT) ctr.shadow_tests += (unsigned long long)tests;
+                    }
+                    alive = bounce_finish<BANDS, COUNT, OPAQUE>(sc, a.p, r, nee, c, visible, &ctr);
+                }
             }
-            const bool pending = hit_wall && c.want_shadow;
-            bool visible = true;
-            if (COOP) {
-                __syncwarp();
-                visible = coop_shadow<COUNT>(sc, pending, c.shadow, lane, ctr);
-            } else if (pending) {
-                int tests = 0;
-                visible = check_vis(sc, c.shadow, COUNT ? &tests : nullptr);
-                if (COUNT) ctr.shadow_tests += (unsigned long long)tests;
-            }
-            if (alive) alive = hit_wall && bounce_finish<BANDS, COUNT, OPAQUE>(sc, a.p, r, nee, c, visible, &ctr);
-            __syncwarp();
+            if (HITS) __syncwarp();  // the deposit starts with a full-mask vote, which reconverges the warp by itself
             if (HITS) {
                 emit_hit(a, direct, id, i, 0);
                 emit_hit(a, nee, id, i, 1);
