@@ -44,6 +44,60 @@ def test_two_rank_allreduce_is_bit_identical_to_one_rank(tmp_path, oracle):
         assert np.array_equal(np.load(tmp_path / f"rank{r}.npy"), whole)
 
 
+class _StubContext:
+    """Stands in for _capi.Context in the set-up protocol of PeerExchange (no GPU here)."""
+
+    def __init__(self, rank, fail_connect_on):
+        self.rank, self.fail_on, self.destroyed, self.connected = rank, fail_connect_on, False, None
+
+    def exchange_create(self, capacity_words):
+        return bytes([self.rank]) * 80
+
+    def exchange_connect(self, rank, world, handles):
+        if rank == self.fail_on:
+            raise RuntimeError("cudaIpcOpenMemHandle: simulated failure")
+        self.connected = list(handles)
+
+    def exchange_destroy(self):
+        self.destroyed = True
+
+    def sync(self):
+        pass
+
+
+def _exchange_worker(rank, world, port, out_dir, fail_on):
+    from realisticaudioraytracing2d_b200.host.sharding import PeerExchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _StubContext(rank, fail_on)
+    try:
+        ex = PeerExchange(ctx, 1000)
+        outcome = "connected" if ctx.connected == [bytes([r]) * 80 for r in range(world)] else "bad handles"
+        ex.close()
+        outcome += "+closed" if ctx.destroyed else ""
+    except RuntimeError as e:
+        outcome = f"raised destroyed={ctx.destroyed}: {e}"
+    with open(os.path.join(out_dir, f"outcome{rank}.txt"), "w") as f:
+        f.write(outcome)
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_is_all_or_nothing(tmp_path):
+    """Either every rank ends up connected or every rank raises (so a caller can fall back consistently)."""
+    for fail_on, sub in ((-1, "ok"), (1, "fail")):
+        d = tmp_path / sub
+        d.mkdir()
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        mp.spawn(_exchange_worker, args=(2, port, str(d), fail_on), nprocs=2, join=True)
+        got = [(d / f"outcome{r}.txt").read_text() for r in range(2)]
+        if fail_on < 0:
+            assert got == ["connected+closed"] * 2
+        else:
+            assert all(g.startswith("raised destroyed=True") and "rank 1: connect" in g for g in got), got
+
+
 def test_allreduce_is_a_noop_without_a_process_group():
     t = torch.arange(8, dtype=torch.int64)
     allreduce_histogram(t)
