@@ -63,3 +63,10 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(_capi.RarError) as e:
         _capi.Context(0)
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_csharp_binding_declares_every_symbol():
+    """csharp/RarNative.cs (the P/Invoke side a maintainer drops into Assets/Script/, not compilable here) names
+    exactly the entry points of include/rar2d.h."""
+    cs = open(os.path.join(ROOT, "csharp", "RarNative.cs")).read()
+    assert sorted(set(re.findall(r"extern\s+\w+\s+(rar_\w+)\s*\(", cs))) == _declared()
