@@ -93,6 +93,8 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_conv_destroy(IntPtr conv);
         [DllImport(Lib)] public static extern int rar_conv_set_ir(IntPtr conv, int stream, [In] float[] ir, int irLen, float scale);
         [DllImport(Lib)] public static extern int rar_conv_set_ir_from_slot(IntPtr conv, int stream, int slot, int accumCount);
+        [DllImport(Lib)] public static extern int rar_conv_update_ir(IntPtr conv, int stream, [In] float[] ir, int irLen, float scale);
+        [DllImport(Lib)] public static extern int rar_conv_update_ir_from_slot(IntPtr conv, int stream, int slot, int accumCount);
         [DllImport(Lib)] public static extern int rar_conv_reset(IntPtr conv);
         [DllImport(Lib)] public static extern int rar_conv_process(IntPtr conv, [In] float[] input, [Out] float[] output);
         [DllImport(Lib)] public static extern int rar_conv_process_device(IntPtr conv, IntPtr dIn, IntPtr dOut);

@@ -320,6 +320,16 @@ RAR_API int rar_conv_destroy(rar_convolver *conv);
 RAR_API int rar_conv_set_ir(rar_convolver *conv, int32_t stream, const float *ir, int32_t ir_len, float scale);
 /* IR of one stream taken on the device from a traced slot (bands == 1), scaled by 1/accum_count. */
 RAR_API int rar_conv_set_ir_from_slot(rar_convolver *conv, int32_t stream, int32_t slot, int32_t accum_count);
+/* Time-varying impulse responses (the ping/pong IR of the streaming path, RayTraceManager.cs:64-123,
+ * inside the partitioned convolver instead of one full convolution per chunk).  Like rar_conv_set_ir /
+ * rar_conv_set_ir_from_slot, but the new response takes effect with a cross-fade over the next block that
+ * rar_conv_process handles: out[n] = y_old[n] + w[n] (y_new[n] - y_old[n]), w[n] = (n + 1) / block, where y_old and
+ * y_new are that block's outputs under the old and the new response with the same input history; later blocks use
+ * the new response alone.  Only the streams being updated pay for the second multiply-accumulate pass.  A second
+ * update before the block is processed replaces the pending response; rar_conv_set_ir cancels it.  Asynchronous. */
+RAR_API int rar_conv_update_ir(rar_convolver *conv, int32_t stream, const float *ir, int32_t ir_len, float scale);
+RAR_API int rar_conv_update_ir_from_slot(rar_convolver *conv, int32_t stream, int32_t slot, int32_t accum_count);
+
 /* Zeroes the delay lines (start of a stream, AudioManager.StartStreaming). */
 RAR_API int rar_conv_reset(rar_convolver *conv);
 /* One block for every stream: in/out are host arrays [n_streams][block].  Blocking; copies included. */

@@ -93,6 +93,8 @@ SYMBOLS = {
     "rar_conv_destroy": (C.c_int, [_p]),
     "rar_conv_set_ir": (C.c_int, [_p, _i32, _p, _i32, _f32]),
     "rar_conv_set_ir_from_slot": (C.c_int, [_p, _i32, _i32, _i32]),
+    "rar_conv_update_ir": (C.c_int, [_p, _i32, _p, _i32, _f32]),
+    "rar_conv_update_ir_from_slot": (C.c_int, [_p, _i32, _i32, _i32]),
     "rar_conv_reset": (C.c_int, [_p]),
     "rar_conv_process": (C.c_int, [_p, _p, _p]),
     "rar_conv_process_device": (C.c_int, [_p, _p, _p]),
@@ -388,6 +390,14 @@ class Convolver:
 
     def set_ir_from_slot(self, stream: int, slot: int, accum_count: int) -> None:
         self._ctx._ck(self._lib.rar_conv_set_ir_from_slot(self._h, stream, slot, accum_count))
+
+    def update_ir(self, stream: int, ir: np.ndarray, scale: float = 1.0) -> None:
+        """rar_conv_update_ir: new response, cross-faded in over the next processed block."""
+        a = np.ascontiguousarray(ir, dtype=np.float32)
+        self._ctx._ck(self._lib.rar_conv_update_ir(self._h, stream, a.ctypes.data if a.size else None, a.size, scale))
+
+    def update_ir_from_slot(self, stream: int, slot: int, accum_count: int) -> None:
+        self._ctx._ck(self._lib.rar_conv_update_ir_from_slot(self._h, stream, slot, accum_count))
 
     def reset(self) -> None:
         self._ctx._ck(self._lib.rar_conv_reset(self._h))

@@ -222,12 +222,15 @@ constexpr int kCmacTy = 4;
 
 // partial[s][split] = sum over the split's partitions of fdl[s][(head - p) mod P] * H[s][p].
 // grid (n_split, S), block (128, kCmacTy).  This is the HBM-bound kernel.
+// LIST: blockIdx.y indexes `list`, the streams whose impulse response is being cross-faded (second pass with the new
+// spectra); otherwise it is the stream itself and the code is the plain hot kernel.
+template <bool LIST>
 __global__ void __launch_bounds__(128 * kCmacTy) stream_cmac_kernel(const float4 *__restrict__ fdl, const float4 *__restrict__ H,
                                                                      float4 *__restrict__ partial, int n_part, int per_split,
-                                                                     int head) {
+                                                                     int head, const int *__restrict__ list) {
     __shared__ float4 red[kCmacTy][128];
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int st = blockIdx.y, split = blockIdx.x;
+    const int st = LIST ? list[blockIdx.y] : (int)blockIdx.y, split = blockIdx.x;
     const int p0 = split * per_split;
     const int p1 = min(p0 + per_split, n_part);
     const float4 *fs = fdl + (size_t)st * n_part * 128 + tx;
@@ -292,6 +295,75 @@ __global__ void __launch_bounds__(64 * kSub) stream_output_kernel(const f2 *__re
             const f2 v = s.a[sub][n];
             float2 *o = reinterpret_cast<float2 *>(out + (size_t)st * kB + 2 * (n - 128));
             *o = make_float2(v.x * scale, v.y * scale);
+        }
+    }
+}
+
+// The output step of a block in which some streams change their impulse response: those streams get
+// out[n] = y_old[n] + w[n] (y_new[n] - y_old[n]), w[n] = (n + 1) / B, y_old from `partial` (spectra in use so far) and
+// y_new from `partial2` (the new spectra, same input history); the others are written as stream_output_kernel does.
+__global__ void __launch_bounds__(64 * kSub) stream_output_fade_kernel(const f2 *__restrict__ partial, const f2 *__restrict__ partial2,
+                                                                        const int *__restrict__ fade, int n_split,
+                                                                        float *__restrict__ out, int n_streams) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int st = blockIdx.x * kSub + sub;
+    load_tables(s);
+    const bool on = st < n_streams;
+    bool any = false;  // block-uniform: the second transform has block-wide barriers
+    for (int k = 0; k < kSub; k++) {
+        const int t = blockIdx.x * kSub + k;
+        if (t < n_streams && fade[t] != 0) any = true;
+    }
+    const bool mine = on && fade[st] != 0;
+    const float scale = 1.0f / (float)kFftM;
+    float y[2][2];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        f2 acc = f2{0.f, 0.f};
+        if (on) {
+            const f2 *src = partial + (size_t)st * n_split * kFftM + i + 64 * m;
+            for (int q = 0; q < n_split; q++) acc = cadd(acc, src[(size_t)q * kFftM]);
+        }
+        s.b[sub][i + 64 * m] = acc;
+    }
+    __syncthreads();
+    irfft512_from_b(s, sub, i);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        const f2 v = s.a[sub][128 + i + 64 * m];
+        y[m][0] = v.x * scale;
+        y[m][1] = v.y * scale;
+    }
+    if (any) {
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            f2 acc = f2{0.f, 0.f};
+            if (mine) {
+                const f2 *src = partial2 + (size_t)st * n_split * kFftM + i + 64 * m;
+                for (int q = 0; q < n_split; q++) acc = cadd(acc, src[(size_t)q * kFftM]);
+            }
+            s.b[sub][i + 64 * m] = acc;
+        }
+        __syncthreads();
+        irfft512_from_b(s, sub, i);
+        if (mine) {
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                const int k0 = 2 * (i + 64 * m);  // sample index inside the block
+                const f2 v = s.a[sub][128 + i + 64 * m];
+                const float w0 = (float)(k0 + 1) * (1.0f / (float)kB), w1 = (float)(k0 + 2) * (1.0f / (float)kB);
+                y[m][0] += w0 * (v.x * scale - y[m][0]);
+                y[m][1] += w1 * (v.y * scale - y[m][1]);
+            }
+        }
+    }
+    if (on) {
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            float2 *o = reinterpret_cast<float2 *>(out + (size_t)st * kB + 2 * (i + 64 * m));
+            *o = make_float2(y[m][0], y[m][1]);
         }
     }
 }
@@ -373,15 +445,33 @@ cudaError_t launch_stream_step(const StreamConv &c, const float *d_in, float *d_
                                                                            c.n_streams, c.n_part, c.head);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    stream_cmac_kernel<<<dim3(c.n_split, c.n_streams), dim3(128, kCmacTy), 0, s>>>(
+    stream_cmac_kernel<false><<<dim3(c.n_split, c.n_streams), dim3(128, kCmacTy), 0, s>>>(
         reinterpret_cast<const float4 *>(c.fdl), reinterpret_cast<const float4 *>(c.H), reinterpret_cast<float4 *>(c.partial),
-        c.n_part, c.part_per_split, c.head);
+        c.n_part, c.part_per_split, c.head, nullptr);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     stream_output_kernel<<<blocks_for(c.n_streams, kSub), 64 * kSub, 0, s>>>(reinterpret_cast<const f2 *>(c.partial), c.n_split,
                                                                             d_out, c.n_streams);
     e = cudaGetLastError();
     if (e == cudaSuccess && launches) *launches += 3;
+    return e;
+}
+
+cudaError_t launch_stream_step_fade(const StreamConv &c, const float2 *H2, float2 *partial2, const int *d_fade, const int *d_list,
+                                    int n_list, const float *d_in, float *d_out, cudaStream_t s, int *launches) {
+    if (c.block != kB || n_list <= 0) return cudaErrorInvalidValue;
+    stream_input_kernel<<<blocks_for(c.n_streams, kSub), 64 * kSub, 0, s>>>(d_in, c.prev, reinterpret_cast<f2 *>(c.fdl),
+                                                                           c.n_streams, c.n_part, c.head);
+    stream_cmac_kernel<false><<<dim3(c.n_split, c.n_streams), dim3(128, kCmacTy), 0, s>>>(
+        reinterpret_cast<const float4 *>(c.fdl), reinterpret_cast<const float4 *>(c.H), reinterpret_cast<float4 *>(c.partial),
+        c.n_part, c.part_per_split, c.head, nullptr);
+    stream_cmac_kernel<true><<<dim3(c.n_split, n_list), dim3(128, kCmacTy), 0, s>>>(
+        reinterpret_cast<const float4 *>(c.fdl), reinterpret_cast<const float4 *>(H2), reinterpret_cast<float4 *>(partial2),
+        c.n_part, c.part_per_split, c.head, d_list);
+    stream_output_fade_kernel<<<blocks_for(c.n_streams, kSub), 64 * kSub, 0, s>>>(
+        reinterpret_cast<const f2 *>(c.partial), reinterpret_cast<const f2 *>(partial2), d_fade, c.n_split, d_out, c.n_streams);
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && launches) *launches += 4;
     return e;
 }
 

@@ -154,6 +154,10 @@ struct rar_convolver {
     DevBuf<float2> H, fdl, partial;
     DevBuf<float> prev, d_in, d_out, d_irf;
     PinnedBuf<float> h_ir;
+    // cross-faded impulse-response updates (allocated on first use)
+    DevBuf<float2> H2, partial2;   // new spectra of the fading streams, their partial sums
+    DevBuf<int> d_fade, d_list;    // [S] flags, compact list of fading streams
+    std::vector<int> fade;         // host copy of the flags
 };
 
 namespace {
@@ -1174,11 +1178,31 @@ int rar_conv_destroy(rar_convolver *cv) {
         }
     cv->H.release(); cv->fdl.release(); cv->partial.release(); cv->prev.release();
     cv->d_in.release(); cv->d_out.release(); cv->d_irf.release(); cv->h_ir.release();
+    cv->H2.release(); cv->partial2.release(); cv->d_fade.release(); cv->d_list.release();
     delete cv;
     return RAR_OK;
 }
 
-int rar_conv_set_ir(rar_convolver *cv, int32_t stream, const float *ir, int32_t ir_len, float scale) {
+// Where the spectra of `stream` go: the active table, or (fade) the table of pending cross-faded updates.
+static int conv_target(rar_convolver *cv, int32_t stream, bool fade, float2 **H) {
+    rar_context *ctx = cv->ctx;
+    StreamConv &c = cv->c;
+    if (cv->fade.empty()) cv->fade.assign(c.n_streams, 0);
+    if (!fade) {
+        cv->fade[stream] = 0;  // a hard set cancels a pending cross-fade of the stream
+        *H = c.H + (size_t)stream * c.n_part * c.block;
+        return RAR_OK;
+    }
+    RAR_CUDA(ctx, cv->H2.reserve((size_t)c.n_streams * c.n_part * c.block));
+    RAR_CUDA(ctx, cv->partial2.reserve((size_t)c.n_streams * c.n_split * c.block));
+    RAR_CUDA(ctx, cv->d_fade.reserve((size_t)c.n_streams));
+    RAR_CUDA(ctx, cv->d_list.reserve((size_t)c.n_streams));
+    cv->fade[stream] = 1;
+    *H = cv->H2.p + (size_t)stream * c.n_part * c.block;
+    return RAR_OK;
+}
+
+static int conv_set_ir_impl(rar_convolver *cv, int32_t stream, const float *ir, int32_t ir_len, float scale, bool fade) {
     if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
     rar_context *ctx = cv->ctx;
     RAR_ENTER(ctx);
@@ -1188,13 +1212,15 @@ int rar_conv_set_ir(rar_convolver *cv, int32_t stream, const float *ir, int32_t 
     for (int i = 0; i < ir_len; i++) cv->h_ir.p[i] = ir[i] * scale;
     if (ir_len > 0)
         RAR_CUDA(ctx, cudaMemcpyAsync(cv->d_irf.p, cv->h_ir.p, (size_t)ir_len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    float2 *H = cv->c.H + (size_t)stream * cv->c.n_part * cv->c.block;
+    float2 *H = nullptr;
+    int rc = conv_target(cv, stream, fade, &H);
+    if (rc != RAR_OK) return rc;
     RAR_CUDA(ctx, launch_ir_spectra(cv->d_irf.p, ir_len, H, cv->c.n_part, cv->c.block, ctx->stream));
     ctx->launches++;
     return RAR_OK;
 }
 
-int rar_conv_set_ir_from_slot(rar_convolver *cv, int32_t stream, int32_t slot, int32_t accum_count) {
+static int conv_set_ir_from_slot_impl(rar_convolver *cv, int32_t stream, int32_t slot, int32_t accum_count, bool fade) {
     if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
     rar_context *ctx = cv->ctx;
     RAR_ENTER(ctx);
@@ -1204,11 +1230,26 @@ int rar_conv_set_ir_from_slot(rar_convolver *cv, int32_t stream, int32_t slot, i
     if (S->bands != 1) return fail(ctx, RAR_ERR_UNSUPPORTED, "convolution needs a broadband (bands == 1) slot");
     if (S->impulse_length > cv->max_ir_len) return fail(ctx, RAR_ERR_INVALID, "slot IR is longer than max_ir_len");
     const float scale = accum_count > 0 ? 1.0f / (float)accum_count : 0.0f;
+    float2 *H = nullptr;
+    int rc = conv_target(cv, stream, fade, &H);
+    if (rc != RAR_OK) return rc;
     RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, cv->d_irf.p, S->impulse_length, scale, ctx->stream));
-    float2 *H = cv->c.H + (size_t)stream * cv->c.n_part * cv->c.block;
     RAR_CUDA(ctx, launch_ir_spectra(cv->d_irf.p, S->impulse_length, H, cv->c.n_part, cv->c.block, ctx->stream));
     ctx->launches += 2;
     return RAR_OK;
+}
+
+int rar_conv_set_ir(rar_convolver *cv, int32_t stream, const float *ir, int32_t ir_len, float scale) {
+    return conv_set_ir_impl(cv, stream, ir, ir_len, scale, false);
+}
+int rar_conv_set_ir_from_slot(rar_convolver *cv, int32_t stream, int32_t slot, int32_t accum_count) {
+    return conv_set_ir_from_slot_impl(cv, stream, slot, accum_count, false);
+}
+int rar_conv_update_ir(rar_convolver *cv, int32_t stream, const float *ir, int32_t ir_len, float scale) {
+    return conv_set_ir_impl(cv, stream, ir, ir_len, scale, true);
+}
+int rar_conv_update_ir_from_slot(rar_convolver *cv, int32_t stream, int32_t slot, int32_t accum_count) {
+    return conv_set_ir_from_slot_impl(cv, stream, slot, accum_count, true);
 }
 
 int rar_conv_reset(rar_convolver *cv) {
@@ -1228,7 +1269,24 @@ int rar_conv_process_device(rar_convolver *cv, const float *d_in, float *d_out) 
     RAR_ENTER(ctx);
     if (!d_in || !d_out) return fail(ctx, RAR_ERR_INVALID, "null device array");
     int launched = 0;
-    RAR_CUDA(ctx, launch_stream_step(cv->c, d_in, d_out, ctx->stream, &launched));
+    std::vector<int> list;
+    for (size_t st = 0; st < cv->fade.size(); st++)
+        if (cv->fade[st]) list.push_back((int)st);
+    if (list.empty()) {
+        RAR_CUDA(ctx, launch_stream_step(cv->c, d_in, d_out, ctx->stream, &launched));
+    } else {
+        // this block cross-fades the listed streams from their current spectra to the pending ones, which then
+        // become current
+        StreamConv &c = cv->c;
+        RAR_CUDA(ctx, cudaMemcpyAsync(cv->d_fade.p, cv->fade.data(), cv->fade.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RAR_CUDA(ctx, cudaMemcpyAsync(cv->d_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RAR_CUDA(ctx, launch_stream_step_fade(c, cv->H2.p, cv->partial2.p, cv->d_fade.p, cv->d_list.p, (int)list.size(), d_in, d_out,
+                                              ctx->stream, &launched));
+        const size_t row = (size_t)c.n_part * c.block;
+        for (int st : list)
+            RAR_CUDA(ctx, cudaMemcpyAsync(c.H + st * row, cv->H2.p + st * row, row * sizeof(float2), cudaMemcpyDeviceToDevice, ctx->stream));
+        cv->fade.assign(cv->fade.size(), 0);
+    }
     ctx->launches += launched;
     cv->c.head = (cv->c.head + 1) % cv->c.n_part;
     return RAR_OK;

@@ -112,6 +112,9 @@ struct StreamConv {
     int head;         // ring slot the next window is written to
 };
 cudaError_t launch_stream_step(const StreamConv &c, const float *d_in, float *d_out, cudaStream_t s, int *launches);
+// The same step while the n_list streams in d_list cross-fade to the spectra in H2 (fade[s] != 0 marks them).
+cudaError_t launch_stream_step_fade(const StreamConv &c, const float2 *H2, float2 *partial2, const int *d_fade, const int *d_list,
+                                    int n_list, const float *d_in, float *d_out, cudaStream_t s, int *launches);
 
 // clip_kernel.cu -- LoadSample (mono mix + linear resample) for a batch of equally shaped clips
 struct ClipPrep {

@@ -177,3 +177,71 @@ def test_streaming_config5_full_size_determinism_and_linearity(ctx):
     assert rel_l2(y1[0, 0], want) <= TOL
     assert cv.bytes_per_block() > 1.9e9
     cv.destroy()
+
+
+def test_streaming_ir_update_with_crossfade(ctx, oracle):
+    """rar_conv_update_ir: the block after an update is y_old + w (y_new - y_old), w[n] = (n+1)/256,
+    with both responses applied to the same input history; later blocks use the new response; streams that were not
+    updated are untouched.  Expected values come from the oracle's direct-form convolution of the whole history."""
+    rng = np.random.default_rng(33)
+    S, B, n_blocks, max_ir = 6, 256, 24, 3000
+    cv = _capi.Convolver(ctx, S, B, max_ir)
+    old = [_ir(L, seed=10 + s) for s, L in enumerate([3000, 1500, 700, 256, 2049, 900])]
+    new = [_ir(L, seed=50 + s) for s, L in enumerate([2000, 3000, 1, 300, 2049, 900])]
+    for s in range(S):
+        cv.set_ir(s, old[s])
+    x = rng.uniform(-1, 1, (S, n_blocks * B)).astype(np.float32)
+    w = (np.arange(B, dtype=np.float32) + 1) / B
+    current = list(old)
+    fades = {5: [1, 3], 6: [1], 12: [0, 1, 2, 3, 4], 13: [5]}       # block -> streams updated just before it
+    out = []
+    for k in range(n_blocks):
+        fading = fades.get(k, [])
+        for s in fading:
+            if k == 6:
+                cv.update_ir(s, old[0])                             # replaced before the block is processed ...
+            cv.update_ir(s, new[s] if current[s] is old[s] else old[s])
+        if k == 13:
+            cv.update_ir(4, old[0])
+            cv.set_ir(4, current[4])                                # ... and a hard set cancels a pending update
+        y = cv.process(x[:, k * B:(k + 1) * B])
+        for s in range(S):
+            hist = x[s, : (k + 1) * B]
+            y_old = oracle.convolve(hist, current[s], 1)[k * B:(k + 1) * B]
+            if s in fading:
+                nxt = new[s] if current[s] is old[s] else old[s]
+                y_new = oracle.convolve(hist, nxt, 1)[k * B:(k + 1) * B]
+                want = y_old + w * (y_new - y_old)
+                current[s] = nxt
+            else:
+                want = y_old
+            assert rel_l2(y[s], want) <= TOL, (k, s)
+        out.append(y)
+    cv.destroy()
+
+
+def test_streaming_ir_update_from_traced_slot(ctx, oracle):
+    """The ping/pong cadence of the reference's streaming path inside the convolver: the IR traced into the other
+    slot replaces the current one with a one-block cross-fade."""
+    sc = scenes.smoll_room()
+    n = 6000
+    ctx.set_walls(sc.walls)
+    irs = []
+    for slot, frame in ((0, 1), (1, 2)):
+        ctx.ir_clear(slot, n, 1)
+        ctx.trace(capi_params(_capi, trace_kwargs(sc, impulse_length=n, rng_state_offset=frame)), slot)
+        irs.append(ctx.ir_read(slot, n))
+    cv = _capi.Convolver(ctx, 1, 256, n)
+    cv.set_ir_from_slot(0, 0, 1)
+    x = np.random.default_rng(4).uniform(-1, 1, (1, 40 * 256)).astype(np.float32)
+    w = (np.arange(256, dtype=np.float32) + 1) / 256
+    for k in range(40):
+        if k == 20:
+            cv.update_ir_from_slot(0, 1, 1)
+        y = cv.process(x[:, k * 256:(k + 1) * 256])[0]
+        hist = x[0, : (k + 1) * 256]
+        a = oracle.convolve(hist, irs[0], 1)[k * 256:(k + 1) * 256]
+        b = oracle.convolve(hist, irs[1], 1)[k * 256:(k + 1) * 256]
+        want = a if k < 20 else (a + w * (b - a) if k == 20 else b)
+        assert rel_l2(y, want) <= TOL, k
+    cv.destroy()
