@@ -236,8 +236,8 @@ RAR_API int rar_exchange_destroy(rar_context *ctx);
  * binary32 without contraction, as the C# computes it: results are bit-exact.
  *   raw  [n_clips][samples][channels] interleaved, as AudioClip.GetData returns it;
  *   out  [n_clips][out_stride]; rar_prepared_length(...) values are written per clip (out_stride >= that).
- * rar_prepare_clips takes host arrays and blocks; rar_prepare_clips_device takes device addresses, enqueues on
- * the context's stream and returns. */
+ * rar_prepare_clips takes host arrays and blocks; rar_prepare_clips_device takes device addresses (d_raw 8-byte
+ * aligned), enqueues on the context's stream and returns. */
 RAR_API int64_t rar_prepared_length(int64_t samples, int32_t clip_frequency, int32_t sample_rate);
 RAR_API int rar_prepare_clips(rar_context *ctx, const float *raw, int64_t samples, int32_t channels,
                               int32_t clip_frequency, int32_t sample_rate, int32_t n_clips, float *out,

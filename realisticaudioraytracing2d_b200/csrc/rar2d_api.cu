@@ -833,6 +833,8 @@ int rar_prepare_clips_device(rar_context *ctx, const void *d_raw, int64_t sample
     RAR_ENTER(ctx);
     int rc = check_clip_args(ctx, d_raw, samples, channels, clip_frequency, sample_rate, n_clips, d_out, out_stride);
     if (rc != RAR_OK) return rc;
+    if (((uintptr_t)d_raw & 7u) != 0 || ((uintptr_t)d_out & 3u) != 0)
+        return fail(ctx, RAR_ERR_INVALID, "device clip arrays must be 8-byte (raw) and 4-byte (out) aligned");
     return prepare_clips_common(ctx, static_cast<const float *>(d_raw), samples, channels, clip_frequency, sample_rate, n_clips,
                                 static_cast<float *>(d_out), out_stride);
 }

@@ -76,6 +76,26 @@ def test_gpu_prepare_clips_edges_and_errors(ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_prepare_clips_device_arrays(ctx, oracle):
+    """rar_prepare_clips_device on arrays already resident in HBM; a misaligned stereo array is refused."""
+    import torch
+    samples, ch, freq, rate, n_clips = 5000, 2, 44100, 48000, 4
+    raw = _clip(samples * n_clips, ch, 3)
+    n = _capi.prepared_length(samples, freq, rate)
+    d_raw = torch.from_numpy(np.concatenate([raw, np.zeros(2, np.float32)])).cuda()
+    d_out = torch.zeros((n_clips, n + 7), dtype=torch.float32, device="cuda")
+    ctx.prepare_clips_device(d_raw.data_ptr(), samples, ch, freq, rate, n_clips, d_out.data_ptr(), n + 7)
+    ctx.sync()
+    got = d_out.cpu().numpy()
+    for k in range(n_clips):
+        want = oracle.load_sample(raw[k * samples * ch:(k + 1) * samples * ch], samples, ch, freq, rate)
+        assert np.array_equal(got[k, :n], want) and not got[k, n:].any()
+    with pytest.raises(_capi.RarError) as e:
+        ctx.prepare_clips_device(d_raw.data_ptr() + 4, samples, ch, freq, rate, n_clips, d_out.data_ptr(), n + 7)
+    assert e.value.code == -1
+
+
+@pytest.mark.gpu
 def test_gpu_prepare_clips_full_size_batch(ctx, oracle):
     """64 stereo clips of 10 s at 44.1 kHz -> 48 kHz (the clip shape of the bench leg), every clip against the oracle."""
     samples, n_clips = 441000, 64
