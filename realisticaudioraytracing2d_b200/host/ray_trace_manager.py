@@ -235,6 +235,66 @@ class RayTraceManager:
         self._ctx = None
 
 
+class RayTraceManagerStreaming(RayTraceManager):
+    """The same component over a convolver that keeps running (not in the reference).
+
+    The reference convolves every chunk from scratch with the IR of that moment and overlap-adds the
+    `inputLen + irLen` results (ProcessChunk, :91-123).  Here one partitioned streaming convolver
+    (rar_conv_*) carries the input history: when a chunk is due its IR slot becomes the convolver's
+    response -- with a one-block cross-fade from the previous one (rar_conv_update_ir_from_slot) -- and
+    the chunk's samples go through in blocks of 256; samples that do not fill a block wait for the next
+    chunk.  Output blocks are pushed to the AudioManager at consecutive offsets.
+    """
+
+    BLOCK = 256
+
+    def StartStreaming(self) -> None:
+        super().StartStreaming()
+        old = getattr(self, "_conv", None)
+        if old is not None:
+            old.destroy()
+        self._conv = _capi.Convolver(self._ctx, 1, self.BLOCK, max(1, self._ir_length()))
+        self._carry = np.zeros(0, dtype=np.float32)
+        self._out_pos = 0
+        self._have_ir = False
+
+    def ProcessChunk(self, sampleOffset: int, chunkLen: int, accumCount: int, ir: int):
+        inputLen = min(chunkLen, len(self.fullInputSamples) - sampleOffset)
+        if inputLen <= 0:
+            return
+        if self._have_ir:
+            self._conv.update_ir_from_slot(0, ir, accumCount)
+        else:
+            self._conv.set_ir_from_slot(0, ir, accumCount)
+            self._have_ir = True
+        data = np.concatenate([self._carry, self.fullInputSamples[sampleOffset: sampleOffset + inputLen]])
+        n_blocks = len(data) // self.BLOCK
+        for b in range(n_blocks):
+            y = self._conv.process(data[b * self.BLOCK:(b + 1) * self.BLOCK][None, :])[0]
+            self.audioManager.PushSamples(y, self._out_pos)
+            self._out_pos += self.BLOCK
+        self._carry = data[n_blocks * self.BLOCK:]
+        if False:  # a coroutine in the base class; nothing to wait for here
+            yield None
+
+    def DrainTail(self) -> None:
+        """Pushes the remaining input and the reverberation tail (zero input for one IR length) through."""
+        n = len(self._carry) + self._ir_length()
+        data = np.concatenate([self._carry, np.zeros(n - len(self._carry) + (-n) % self.BLOCK, dtype=np.float32)])
+        for b in range(len(data) // self.BLOCK):
+            y = self._conv.process(data[b * self.BLOCK:(b + 1) * self.BLOCK][None, :])[0]
+            self.audioManager.PushSamples(y, self._out_pos)
+            self._out_pos += self.BLOCK
+        self._carry = np.zeros(0, dtype=np.float32)
+
+    def OnDestroy(self) -> None:
+        conv = getattr(self, "_conv", None)
+        if conv is not None:
+            conv.destroy()
+            self._conv = None
+        super().OnDestroy()
+
+
 class RayTraceManagerComplex(RayTraceManager):
     """The offline use-case of Assets/Script/RayTraceManagerComplex.cs: BakeAudio (:170-227) convolves the
     whole clip with the single accumulated IR in one call and PlayResult (:228-245) peak-normalises it.

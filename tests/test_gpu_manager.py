@@ -116,3 +116,55 @@ def test_load_samples_batched_equals_load_sample(ctx):
     got = m.LoadSamples(clips)
     for c, g in zip(clips, got):
         assert np.array_equal(g, m.LoadSample(c))
+
+
+def test_streaming_manager_with_a_running_convolver(ctx, oracle):
+    """RayTraceManagerStreaming: the chunk cadence of the reference over one running partitioned convolver whose
+    response is switched, with a one-block cross-fade, to the IR accumulated since the previous chunk.  Replay the
+    schedule with the oracle: block g is the direct-form convolution of the whole input so far with the response
+    of the moment (blend of old and new in the first block after a switch)."""
+    from realisticaudioraytracing2d_b200.host.ray_trace_manager import RayTraceManagerStreaming
+    m = _manager(ctx, RayTraceManagerStreaming)
+    m.rayCount, m.reverbDuration = 2000, 0.25
+    n_ir = 12000
+    m.audioManager = AudioManager(outputSampleRate=48000)
+    clip = scenes.synthetic_clip(12000)
+    m.inputClip = AudioClip(clip, 1, 48000)
+    m.loop = False
+    m.Start()
+    m.StartStreaming()
+    sc = scenes.smoll_room()
+    hist = np.zeros(n_ir, np.int64)
+    frames_in_ir = 0
+    irs, fed = [], []                                               # response and input length after each chunk
+    for step in range(18):
+        m.Update()
+        P = oracle.make_params(source_x=-18.0, source_y=9.0, listener_x=0.0, listener_y=-3.68, ray_count=2000,
+                               max_bounce_count=5, rng_state_offset=m.frameCount, impulse_length=n_ir, debug_ray_count=100)
+        oracle.trace(sc.walls.view(oracle.SEGMENT_DTYPE), P, hist=hist)
+        frames_in_ir += 1
+        before = m.nextStreamingOffset
+        m.FixedUpdate()
+        if m.nextStreamingOffset != before and before < len(clip):
+            irs.append(oracle.ir_to_float(hist) / np.float32(max(1, frames_in_ir)))
+            fed.append(min(before + 4800, len(clip)))
+            hist[:] = 0
+            frames_in_ir = 0
+    assert fed == [4800, 9600, 12000] and m._out_pos == (12000 // 256) * 256 and len(m._carry) == 12000 % 256
+    m.DrainTail()
+    x = np.concatenate([clip, np.zeros(m._out_pos - len(clip), np.float32)])
+    w = (np.arange(256, dtype=np.float32) + 1) / 256
+    full = [oracle.convolve(x, h, 1)[: m._out_pos] for h in irs]
+    expect = np.zeros(m._out_pos, np.float32)
+    first_block = [0] + [f // 256 for f in fed[:-1]]                 # first block processed under response c
+    for g in range(m._out_pos // 256):
+        c = max(k for k, fb in enumerate(first_block) if fb <= g)
+        blk = slice(g * 256, (g + 1) * 256)
+        if c > 0 and g == first_block[c]:
+            expect[blk] = full[c - 1][blk] + w * (full[c][blk] - full[c - 1][blk])
+        else:
+            expect[blk] = full[c][blk]
+    got = m.audioManager.ringBuffer[: m._out_pos]
+    assert np.abs(expect).max() > 0
+    assert rel_l2(got, expect) <= 1e-4
+    m.OnDestroy()
