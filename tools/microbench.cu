@@ -51,6 +51,46 @@ __global__ void __launch_bounds__(256) lds_bcast(float *out, int n) {
     if (s == 12345.678f) out[0] = s;
 }
 
+// L2 -> shared memory bulk copy (TMA 1-D, cp.async.bulk + mbarrier), the way trace_kernel.cu stages the wall
+// planes: every CTA copies the same `bytes`-long, L2-resident region `reps` times, two copies in flight.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(256) tma_stage(const float4 *src, unsigned bytes, int reps, float *out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long bar[2];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; b++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[b])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    float s = 0;
+    for (int r = 0; r < reps + 1; r++) {
+        if (r < reps && threadIdx.x == 0) {
+            const int b = r & 1;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[b])), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + (size_t)b * bytes)),
+                         "l"(src), "r"(bytes), "r"(smem_u32(&bar[b]))
+                         : "memory");
+        }
+        if (r > 0) {  // wait for copy r-1 while copy r is in flight
+            const int b = (r - 1) & 1;
+            const unsigned parity = ((r - 1) >> 1) & 1;
+            unsigned ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(ok)
+                    : "r"(smem_u32(&bar[b])), "r"(parity)
+                    : "memory");
+            }
+            s += reinterpret_cast<const float *>(smem + (size_t)b * bytes)[threadIdx.x];
+            __syncthreads();  // the buffer is reused two copies later
+        }
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
 template <class F>
 double time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -97,5 +137,19 @@ int main() {
     const double lds = (double)blocks * 256 * ITER * 16.0;
     printf("LDS.128 broadcast  %8.3f ms  %7.2f T lane-loads/s  (%.3f warp-LDS/clk/SM)\n", l, lds / (l * 1e-3) / 1e12,
            lds / 32.0 / (l * 1e-3) / (sms * 1.965e9));
+    // L2 -> smem staging: 64 KB per copy (two buffers = 128 KB of shared memory per CTA, one CTA per SM), 200 copies
+    {
+        const unsigned bytes = 64 << 10;
+        const int reps = 200;
+        float4 *src;
+        cudaMalloc(&src, bytes);
+        cudaMemset(src, 0, bytes);
+        cudaFuncSetAttribute(tma_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bytes);
+        double t = time_ms([&] { tma_stage<<<sms, 256, 2 * bytes>>>(src, bytes, reps, out); });
+        const double total = (double)sms * reps * bytes;
+        printf("TMA L2->smem bulk  %8.3f ms  %7.2f TB/s aggregate  (%.1f B/clk/SM at 1.965 GHz)\n", t, total / (t * 1e-3) / 1e12,
+               total / (t * 1e-3) / (sms * 1.965e9));
+        cudaFree(src);
+    }
     return 0;
 }
