@@ -11,6 +11,13 @@ range of a dispatch of N x 1 Mi rays (weak scaling).  The same line carries the 
 (config 5: 256 streams x 10 s IRs per GPU, block 256) under "conv", a large-scene trace (config 3
 geometry, reduced ray count) under "maze", the roofline of the dominant kernel and the CPU baseline.
 
+Legs added for the multi-GPU record (N >= 1, same launch): `strong.c3` -- BASELINE config 3 geometry (10 000 walls,
+8 bands, 64 bounces, brute force) with a FIXED total of 4 849 664 rays split over the N ranks by contiguous ray-id
+range, two-shot all-reduce of the 3.07 MB histogram -- and `strong.c2` -- config 2 with a fixed total of 1 Mi rays
+(the latency regime).  Both compare the SHA-256 of the all-reduced histogram with the hash the CPU oracle minted for
+the unsharded dispatch (tests/golden/strong_scaling.json): `parity_ok`.  `unsharded_equal` does the same for the weak
+leg against a single-GPU trace of all N ranges.
+
 `--impl reference` times the CPU oracle (the only CPU implementation of this path that exists: the
 reference itself is HLSL compute run by Unity) on the host cores, on bounded samples of the same
 workload.  It is the one place besides cpu_baseline where bench.py executes oracle/.
@@ -36,6 +43,25 @@ WORKLOAD = "config2: synthetic shoebox 10x6 m (4 walls), 1048576 rays x 32 bounc
 RAYS_PER_GPU = 1 << 20
 BOUNCES = 32
 FLOPS_PER_TEST = 20.0  # ~20 fp32 lane-ops per ray-segment test
+IR_BINS = 48000
+
+
+L2_NOTE = "flushed between timed steps (256 MiB write); per-step CUDA events summed"
+EXCHANGE_PEER = ("all-reduce(sum,int64) of the histogram by the library's peer-memory kernel "
+                 "(CUDA IPC over NVLink, one launch per rank)")
+EXCHANGE_NCCL = "ncclAllReduce(sum,int64) of the histogram"
+
+
+def _config(n_gpus: int, use_nccl: bool = False) -> dict:
+    """The `config` object BOTH arms print, key for key and value for value (the driver compares them); what is
+    specific to the CPU arm is said in its `config_note`."""
+    return {"workload": WORKLOAD, "rays_total": RAYS_PER_GPU * n_gpus, "bounces": BOUNCES, "walls": 4, "ir_bins": IR_BINS,
+            "l2": L2_NOTE, "exchange": "none" if n_gpus == 1 else (EXCHANGE_NCCL if use_nccl else EXCHANGE_PEER)}
+
+
+def _strong_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "strong_scaling.json")) as f:
+        return json.load(f)
 
 
 def _traffic(kernel: str, key: str = "bytes"):
@@ -144,7 +170,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+        "config": _config(args.gpus, os.environ.get("RAR_BENCH_EXCHANGE", "peer") == "nccl"),
+        "config_note": "CPU arm of the same workload: one host, no GPU, no exchange; each step is the bounded sample named in "
+                       "cpu_baseline.sample (the `l2` and `exchange` entries of config describe the GPU arm it is compared with)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"rays [0,{rays}) of the dispatch x {BOUNCES} bounces per step, OpenMP over rays"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -200,7 +228,7 @@ def run_ours(args):
     ex = None
     if world > 1 and not use_nccl:
         try:
-            ex = sharding.PeerExchange(ctx, n_bins)
+            ex = sharding.PeerExchange(ctx, n_bins * 8)          # room for the 8-band histogram of the strong.c3 leg
         except RuntimeError as e:   # raised on every rank or on none: CUDA IPC is unavailable between these processes
             sys.stderr.write(f"[bench] {e}; using ncclAllReduce for the exchange\n")
             use_nccl = True
@@ -344,9 +372,23 @@ def run_ours(args):
     value = tests_all / (ms * 1e-3)
     e2e_value = tests_all / (e2e_ms * 1e-3)
 
-    # ---- secondary measurements on rank-local data (reported by rank 0) ------------------------------
+    # ---- secondary measurements (reported by rank 0) ----------------------------------------------------
     extra = {}
     fp32_peak = ctx.measure_fp32_peak()
+    env = dict(ctx=ctx, capi=_capi, scenes=scenes, torch=torch, dist=dist, sharding=sharding, stream=stream, flush=flush, dev=dev,
+               rank=rank, world=world, ex=ex, use_nccl=use_nccl, barrier=barrier, fp32_peak=fp32_peak)
+    try:
+        extra["unsharded_equal"] = check_unsharded(env, sc, params, step, hist_t, n_bins)
+    except Exception as e:  # keep the headline even if a secondary leg fails
+        extra["unsharded_equal"] = {"error": str(e)}
+    try:
+        extra["strong"] = bench_strong(env)
+    except Exception as e:
+        extra["strong"] = {"error": str(e)}
+    try:
+        extra["listeners"] = bench_listeners(env)
+    except Exception as e:
+        extra["listeners"] = {"error": str(e)}
     try:
         extra["maze"] = bench_maze(ctx, _capi, scenes, torch, stream, flush, fp32_peak)
     except Exception as ex:  # keep the headline even if a secondary leg fails
@@ -389,25 +431,22 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / len(frames), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_total": RAYS_PER_GPU * world, "bounces": BOUNCES, "walls": 4,
-                       "ir_bins": n_bins, "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed",
-                       "exchange": "none" if world == 1 else
-                                   ("ncclAllReduce(sum,int64) of the histogram" if use_nccl else
-                                    "all-reduce(sum,int64) of the histogram by the library's peer-memory kernel "
-                                    "(CUDA IPC over NVLink, one launch per rank)")},
+            "config": _config(world, use_nccl),
+            "value_executed": tests_exec_all / (ms * 1e-3),
             "ir_build_ms": ms / len(frames),
             "tests_per_step": tests_all / len(frames),
             "tests_executed_per_step": tests_exec_all / len(frames),
             "counting_rule": "value counts the intersect() evaluations the reference algorithm performs for this input "
                              "(SURVEY 8d: nearest-hit tests + early-exit-aware shadow tests, counted by the kernel and checked "
                              "against the oracle); the kernel evaluates fewer (tests_executed_per_step) because it skips shadow "
-                             "rays whose estimate cannot pass the deposit threshold; roofline.achieved uses the executed count",
+                             "rays whose estimate cannot pass the deposit threshold; value_executed and roofline.achieved use the "
+                             "executed count -- quote value_executed as the absolute rate of work done",
             "wall_ms_per_step_incl_flush": t_wall / len(frames) * 1e3,
             "roofline": {"bound": "fp32-issue", "achieved": ach, "peak": peak, "unit": "Tlaneop/s", "frac": ach / peak,
                          "traffic": _traffic("trace_deposit_kernel"), "kernel": "trace_deposit_kernel",
                          "ncu_issue_slot_utilisation_pct": _traffic("trace_deposit_kernel", "sm_inst_issued_pct_of_peak"),
-                         "note": f"{FLOPS_PER_TEST:g} fp32 lane-ops per ray-segment test (SURVEY 8d) x tests EXECUTED per launch / "
-                                 "CUDA-event duration; peak = FFMA issue rate measured in this run (rar_measure_fp32_peak); "
+                         "note": f"{FLOPS_PER_TEST:g} fp32 lane-ops per ray-segment test (SURVEY 8d) x tests EXECUTED per launch "
+                                 "(value_executed is the same count per second, whole job) / CUDA-event duration; peak = FFMA issue rate measured in this run (rar_measure_fp32_peak); "
                                  "HBM traffic is negligible for this kernel (scene 160 B, histogram 384 KB, L2 resident)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(walls_host.nbytes + 88),
@@ -427,6 +466,199 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     ctx.destroy()
+
+
+def _sha(a) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _all_true(env, flag: bool) -> bool:
+    """Logical AND of `flag` over the ranks."""
+    if env["world"] == 1:
+        return bool(flag)
+    t = env["torch"].tensor([1.0 if flag else 0.0], dtype=env["torch"].float64, device=env["dev"])
+    env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MIN)
+    return bool(float(t[0]) == 1.0)
+
+
+def _max_over_ranks(env, values):
+    if env["world"] == 1:
+        return [float(v) for v in values]
+    t = env["torch"].tensor([float(v) for v in values], dtype=env["torch"].float64, device=env["dev"])
+    env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def _sum_over_ranks(env, values):
+    if env["world"] == 1:
+        return [float(v) for v in values]
+    t = env["torch"].tensor([float(v) for v in values], dtype=env["torch"].float64, device=env["dev"])
+    env["dist"].all_reduce(t, op=env["dist"].ReduceOp.SUM)
+    return [float(v) for v in t]
+
+
+def check_unsharded(env, sc, params, step, hist_t, n_bins):
+    """Multi-GPU parity of the weak-scaled headline leg: one more step on a fixed frame (every rank traces its own
+    ray range, then the all-reduce), after which rank 0 ALONE traces all N ranges into a second slot and compares
+    the two histograms; the ranks' copies of the all-reduced histogram are compared through their hashes."""
+    ctx, capi, torch, dist, world, rank = env["ctx"], env["capi"], env["torch"], env["dist"], env["world"], env["rank"]
+    frame = 777
+    step(frame)
+    torch.cuda.synchronize()
+    mine = ctx.ir_read_fixed(0, n_bins)
+    equal = True
+    if rank == 0:
+        ctx.ir_clear(1, n_bins, 1)
+        total = RAYS_PER_GPU * world
+        for r in range(world):
+            lo, hi = env["sharding"].shard_range(total, r, world)
+            ctx.trace(capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
+                                             BOUNCES, frame, sc.ray_count, 100, sc.sample_rate, n_bins, 1, 1.0, 0, lo, hi), 1)
+        equal = bool(np.array_equal(ctx.ir_read_fixed(1, n_bins), mine)) and bool(mine.any())
+    digests = [_sha(mine)]
+    if world > 1:
+        digests = [None] * world
+        dist.all_gather_object(digests, _sha(mine))
+    return {"equal": _all_true(env, equal), "ranks_identical": len(set(digests)) == 1, "hist_sha256": digests[0],
+            "what": f"all-reduced histogram of {world} x {RAYS_PER_GPU} rays (frame {frame}) == rank 0 tracing all {world} ranges alone"}
+
+
+STRONG_LEGS = {   # must equal tests/golden/make_strong_golden.py LEGS
+    "c3": dict(kind="maze", walls=10000, rays=148 * 1024 * 32, bounces=64, bands=8, frame=1, reps=3, slot=4),
+    "c2": dict(kind="shoebox", walls=4, rays=1 << 20, bounces=32, bands=1, frame=1, reps=10, slot=5),
+}
+
+
+def bench_strong(env):
+    """STRONG scaling: a fixed dispatch split over the N ranks by contiguous ray-id range, one all-reduce of the
+    histogram per step.  c3 = BASELINE config 3 geometry (10 000-wall maze, 8 bands, 64 bounces, brute force) with
+    4 849 664 rays in total; c2 = config 2 with 1 Mi rays in total (latency regime).  The SHA-256 of the all-reduced
+    histogram is compared with the one the CPU oracle produced for the unsharded dispatch."""
+    ctx, capi, scenes, torch, dist = env["ctx"], env["capi"], env["scenes"], env["torch"], env["dist"]
+    world, rank, stream, flush, ex, use_nccl = env["world"], env["rank"], env["stream"], env["flush"], env["ex"], env["use_nccl"]
+    golden = _strong_golden()
+    out = {}
+    for name, leg in STRONG_LEGS.items():
+        g = golden.get(name)
+        if g is None or any(g[k] != leg[k] for k in ("kind", "walls", "rays", "bounces", "bands", "frame")):
+            out[name] = {"error": "tests/golden/strong_scaling.json does not describe this dispatch"}
+            continue
+        if leg["kind"] == "maze":
+            sc = scenes.maze(n_segments=leg["walls"], ray_count=leg["rays"], max_bounces=leg["bounces"], bands=8)
+        else:
+            sc = scenes.shoebox(ray_count=leg["rays"], max_bounces=leg["bounces"])
+        n, bands, slot = sc.impulse_length, leg["bands"], leg["slot"]
+        lo, hi = env["sharding"].shard_range(leg["rays"], rank, world)
+        ctx.set_walls(sc.walls)
+        if bands > 1:
+            ctx.set_wall_band_absorption(sc.band_absorption)
+        ctx.ir_clear(slot, n, bands)
+        hist_t = env["sharding"].DeviceHistogram(ctx, slot, env["dev"]).tensor if (world > 1 and use_nccl) else None
+
+        def prm(flags=0, b=lo, e=hi, bounces=leg["bounces"]):
+            return capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
+                                          bounces, leg["frame"], leg["rays"], 0, sc.sample_rate, n, bands, 1.0, flags, b, e)
+
+        def one_step():
+            ctx.ir_clear(slot, n, bands)
+            ctx.trace(prm(), slot)
+            if world > 1:
+                if use_nccl:
+                    env["sharding"].allreduce_histogram(hist_t)
+                else:
+                    ex.allreduce(slot)
+
+        ctx.trace(prm(b=lo, e=min(hi, lo + 4096), bounces=2), slot)      # first launch of this kernel variant
+        one_step()                                                        # warm-up at full size
+        env["barrier"]()
+        evs = []
+        for _ in range(leg["reps"]):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            one_step()
+            e1.record(stream)
+            evs.append((e0, e1))
+        env["barrier"]()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        digest = _sha(ctx.ir_read_fixed(slot, n * bands))
+        # the tests the production kernel evaluates on this rank's share (roofline numerator)
+        ctx.get_counters(reset=True)
+        ctx.ir_clear(slot, n, bands)
+        ctx.trace(prm(capi.RAR_FLAG_COUNT_TESTS | capi.RAR_FLAG_COUNT_EXECUTED), slot)
+        c = ctx.get_counters(reset=True)
+        (ms,) = _max_over_ranks(env, [ms])
+        (executed,) = _sum_over_ranks(env, [c["nearest_tests"] + c["shadow_tests"]])
+        tests = g["counters"]["nearest_tests"] + g["counters"]["shadow_tests"]
+        parity = _all_true(env, digest == g["hist_sha256"])
+        res = {"workload": f"{sc.name}: {leg['walls']} walls, {leg['rays']} rays in total x {leg['bounces']} bounces, {bands} band(s), "
+                           f"brute force; ray ids split over {world} GPU(s), all-reduce of {n * bands * 8} bytes",
+               "n_gpus": world, "ir_build_ms": ms, "steps": leg["reps"], "tests": tests, "tests_executed": executed,
+               "tests_per_s": tests / (ms * 1e-3), "tests_executed_per_s": executed / (ms * 1e-3),
+               "hist_sha256": digest, "golden_sha256": g["hist_sha256"], "parity_ok": parity,
+               "golden": "tests/golden/strong_scaling.json (minted by the CPU oracle, unsharded)"}
+        if env["fp32_peak"]:
+            ach = executed / world * FLOPS_PER_TEST / (ms * 1e-3) / 1e12
+            res["roofline"] = {"bound": "fp32-issue", "achieved": ach, "peak": env["fp32_peak"] / 1e12, "unit": "Tlaneop/s",
+                               "frac": ach / (env["fp32_peak"] / 1e12), "traffic": None, "kernel": "trace_deposit_kernel",
+                               "note": "per GPU: tests executed / N x 20 lane-ops / step time (exchange included)"}
+        out[name] = res
+    return out
+
+
+def bench_listeners(env):
+    """BASELINE config 4 (batched auralisation), one GPU's share: 128 listener positions (this rank's contiguous
+    range of the 32 x 32 grid) in the 2 000-wall scene, 4 Mi rays x 5 bounces each, fused listener kernel, one IR
+    slot per listener, no collective (listeners shard across GPUs)."""
+    ctx, capi, scenes, torch, stream = env["ctx"], env["capi"], env["scenes"], env["torch"], env["stream"]
+    world, rank = env["world"], env["rank"]
+    per_gpu, rays, bounces, walls, first = 128, 1 << 22, 5, 2000, 100
+    sc = scenes.maze(n_segments=walls, ray_count=rays, max_bounces=bounces, bands=8)
+    n = sc.impulse_length
+    gx, gy = np.meshgrid(np.linspace(8, 92, 32), np.linspace(8, 92, 32))
+    grid = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.float32)
+    mine = grid[(per_gpu * rank) % 1024:(per_gpu * rank) % 1024 + per_gpu]
+    ctx.set_walls(sc.walls)
+
+    def clear():
+        for l in range(per_gpu):
+            ctx.ir_clear(first + l, n, 1)
+
+    def prm(flags=0, r=rays, listener=(0.0, 0.0)):
+        return capi.make_trace_params(sc.source, listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain, bounces, 1,
+                                      r, 0, sc.sample_rate, n, 1, 1.0, flags, 0, 0)
+    clear()
+    ctx.trace_listeners(prm(r=4096), mine, first)               # warm-up
+    clear()
+    env["barrier"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.trace_listeners(prm(), mine, first)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    h0 = ctx.ir_read_fixed(first, n)
+    ctx.ir_clear(first + per_gpu, n, 1)                        # listener 0 again as a plain single-listener trace
+    ctx.trace(prm(listener=(float(mine[0, 0]), float(mine[0, 1]))), first + per_gpu)
+    same = bool(np.array_equal(ctx.ir_read_fixed(first + per_gpu, n), h0)) and bool(h0.any())
+    clear()
+    ctx.get_counters(reset=True)
+    ctx.trace_listeners(prm(capi.RAR_FLAG_COUNT_TESTS | capi.RAR_FLAG_COUNT_EXECUTED), mine, first)
+    c = ctx.get_counters(reset=True)
+    executed = c["nearest_tests"] + c["shadow_tests"]
+    (ms,) = _max_over_ranks(env, [ms])
+    (executed_all,) = _sum_over_ranks(env, [executed])
+    res = {"workload": f"config4 share: {per_gpu} listeners per GPU x {rays} rays x {bounces} bounces, {walls}-wall scene, "
+                       f"{n} bins per listener, fused listener kernel (each ray traced once per launch)",
+           "n_gpus": world, "listeners_total": per_gpu * world, "ms": ms, "ms_per_listener": ms / per_gpu,
+           "tests_executed": executed_all, "tests_executed_per_s": executed_all / (ms * 1e-3),
+           "fused_equals_single_listener_trace": _all_true(env, same)}
+    if env["fp32_peak"]:
+        ach = executed * FLOPS_PER_TEST / (ms * 1e-3) / 1e12
+        res["roofline"] = {"bound": "fp32-issue", "achieved": ach, "peak": env["fp32_peak"] / 1e12, "unit": "Tlaneop/s",
+                           "frac": ach / (env["fp32_peak"] / 1e12), "traffic": None, "kernel": "trace_listeners_kernel"}
+    return res
 
 
 def bench_maze(ctx, _capi, scenes, torch, stream, flush, fp32_peak=None):
@@ -450,17 +682,24 @@ def bench_maze(ctx, _capi, scenes, torch, stream, flush, fp32_peak=None):
         ctx.trace(prm(_capi.RAR_FLAG_COUNT_TESTS | _capi.RAR_FLAG_COUNT_EXECUTED), 2)
         c = ctx.get_counters(reset=True)
         tests_exec = c["nearest_tests"] + c["shadow_tests"]   # what the production kernel evaluates (skipped shadow rays)
-        best = 1e30
-        for _ in range(3):
-            flush.zero_()
+        def timed(flags, reps=5):
+            """Mean launch time over `reps` launches (after one untimed launch), L2 flushed before each."""
             ctx.ir_clear(2, n, bands)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            ctx.trace(prm(), 2)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        out[f"bands{bands}"] = {"tests": tests, "ms": best, "tests_per_s": tests / (best * 1e-3)}
+            ctx.trace(prm(flags), 2)
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                ctx.ir_clear(2, n, bands)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.trace(prm(flags), 2)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / reps
+        best = timed(0)
+        out[f"bands{bands}"] = {"tests": tests, "ms": best, "launches_averaged": 5, "tests_per_s": tests / (best * 1e-3),
+                                "tests_executed_per_s": tests_exec / (best * 1e-3)}
         if fp32_peak:
             # the wall-dominated regime: nearly every instruction of the kernel belongs to a wall test, so the
             # 20-op rule of SURVEY 8(d) describes the kernel; achieved uses the tests EXECUTED
@@ -471,16 +710,7 @@ def bench_maze(ctx, _capi, scenes, torch, stream, flush, fp32_peak=None):
                                                "kernel": "trace_deposit_kernel (1024-thread cooperative variant)"}
         # the same IR through the optional uniform grid (identical histogram, far fewer tests evaluated)
         ref = ctx.ir_read_fixed(2, n * bands)
-        gbest = 1e30
-        for _ in range(3):
-            flush.zero_()
-            ctx.ir_clear(2, n, bands)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            ctx.trace(prm(_capi.RAR_FLAG_USE_GRID), 2)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            gbest = min(gbest, e0.elapsed_time(e1))
+        gbest = timed(_capi.RAR_FLAG_USE_GRID)
         out[f"bands{bands}"]["grid_ms"] = gbest
         out[f"bands{bands}"]["grid_identical"] = bool(np.array_equal(ctx.ir_read_fixed(2, n * bands), ref))
     out["workload"] = f"config3 geometry: 10000-wall maze, {sc.ray_count} rays x 16 bounces (reduced ray count)"
@@ -518,8 +748,31 @@ def bench_config1(ctx, _capi, scenes, torch, stream):
     e1.record(stream)
     torch.cuda.synchronize()
     batched_ms = e0.elapsed_time(e1) / 100
+    ctx.get_counters(reset=True)
+    ctx.ir_clear(4, n, 1)
+    ctx.trace(_capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain, sc.max_bounces,
+                                      10, sc.ray_count, 100, sc.sample_rate, n, 1, 1.0, _capi.RAR_FLAG_COUNT_TESTS), 4)
+    c = ctx.get_counters(reset=True)
+    tests_per_frame = c["nearest_tests"] + c["shadow_tests"]      # frame 10, counted by the kernel
     clip = scenes.synthetic_clip()
     chunk = clip[:4800]
+    # one whole frame of the reference's real-time loop through host buffers (RayTraceManager.cs:50-53,64-123):
+    # wall upload -> clear -> trace -> 4800-sample chunk convolved with the fresh IR -> output back on the host
+    walls_host = np.ascontiguousarray(sc.walls)
+
+    def frame(f):
+        ctx.set_walls(walls_host)
+        ctx.ir_clear(3, n, 1)
+        ctx.trace(prm(f), 3)
+        return ctx.convolve(3, chunk, 1, n)
+    for f in range(3):
+        frame(300 + f)
+    t0 = time.perf_counter()
+    for f in range(30):
+        frame(400 + f)
+    frame_e2e_ms = (time.perf_counter() - t0) / 30 * 1e3
+    for f in range(reps + 3):
+        ctx.trace(prm(500 + f), 3)
     ctx.convolve(3, chunk, reps + 3, n)
     t0 = time.perf_counter()
     for _ in range(20):
@@ -531,7 +784,10 @@ def bench_config1(ctx, _capi, scenes, torch, stream):
         ctx.convolve(3, clip, reps + 3, n)
     clip_ms = (time.perf_counter() - t0) / 10 * 1e3
     return {"workload": "config1: SmollRoom 20 walls, 15000 rays x 5 bounces per frame; 1.5 s IR; 4800-sample chunk / 42624-sample clip",
-            "ir_build_ms_per_frame": frame_ms, "ir_build_ms_per_frame_batched_x10": batched_ms, "tests_per_frame": 2572899, "tests_per_s": 2572899 / (frame_ms * 1e-3),
+            "ir_build_ms_per_frame": frame_ms, "ir_build_ms_per_frame_batched_x10": batched_ms, "tests_per_frame": tests_per_frame,
+            "tests_per_s": tests_per_frame / (frame_ms * 1e-3),
+            "frame_e2e_ms": frame_e2e_ms, "frame_e2e": "host walls -> clear -> trace -> 4800-sample chunk convolved with the fresh 72000-tap IR -> "
+                                                        "76800 output samples on the host; wall clock per frame, blocking",
             "chunk_convolve_e2e_ms": chunk_ms, "chunk_realtime_factor": 100.0 / chunk_ms,
             "clip_convolve_e2e_ms": clip_ms, "clip_samples_per_s": (len(clip) + n) / (clip_ms * 1e-3)}
 

@@ -348,6 +348,14 @@ RAR_API int rar_device_info(rar_context *ctx, int32_t *sm_count, int32_t *sm_clo
  * fused multiply-add = 1 lane-op): the denominator of the ray stage's roofline. */
 RAR_API int rar_measure_fp32_peak(rar_context *ctx, double *lane_ops_per_s);
 
+/* Device self-test of the ray stage's arithmetic contract: the kernels for opaque, coordinate-bounded scenes evaluate
+ * 1/x, sqrt(x) and a/b as the fast paths of the correctly rounded operations with ONE range test per group of
+ * operations instead of one guard per operation (csrc/rar_math.cuh).  This compares those forms with the correctly
+ * rounded device intrinsics, bit for bit, on n_samples pseudo-random operand sets spread over the whole admitted
+ * exponent range; mismatches[0..4] receive the number of differing results (reciprocal, square root, division,
+ * division by a launch-invariant divisor, range test).  All zeros is the only passing result.  Blocking. */
+RAR_API int rar_selftest_arithmetic(rar_context *ctx, int64_t n_samples, uint32_t seed, uint64_t *mismatches);
+
 /* Number of kernels this library has launched on the context since creation (bench: gpu_launches). */
 RAR_API int64_t rar_launch_count(const rar_context *ctx);
 

@@ -101,6 +101,7 @@ SYMBOLS = {
     "rar_conv_bytes_per_block": (_i64, [_p]),
     "rar_device_info": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "rar_measure_fp32_peak": (C.c_int, [_p, C.POINTER(C.c_double)]),
+    "rar_selftest_arithmetic": (C.c_int, [_p, _i64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "rar_launch_count": (_i64, [_p]),
 }
 
@@ -346,6 +347,12 @@ class Context:
         v = C.c_double()
         self._ck(self._lib.rar_measure_fp32_peak(self._h, C.byref(v)))
         return v.value
+
+    def selftest_arithmetic(self, n_samples: int, seed: int = 1) -> list:
+        """rar_selftest_arithmetic: mismatch counts [rcp, sqrt, div, div-by-constant, range test]; all zero = pass."""
+        m = (C.c_uint64 * 5)()
+        self._ck(self._lib.rar_selftest_arithmetic(self._h, n_samples, seed & 0xFFFFFFFF, m))
+        return [int(v) for v in m]
 
     def launch_count(self) -> int:
         return int(self._lib.rar_launch_count(self._h))

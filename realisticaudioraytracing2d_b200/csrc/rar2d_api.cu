@@ -133,6 +133,7 @@ struct rar_context {
     DevBuf<f4> d_grid_geo;
     bool grid_valid = false;
     bool walls_are_opaque = false;  // no wall has transmission > 0
+    bool walls_are_bounded = false; // every coordinate finite and within 2^30 (rar_layout.h walls_bounded)
 
     std::vector<Slot> slots;
     DevBuf<unsigned long long> d_counters;  // 5 counters + 1 hit count
@@ -264,6 +265,7 @@ void fill_launch(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     a.band_valid = p->bands > 8 ? 8 : p->bands;
     a.p = ray_consts(*p);
     a.opaque = ctx->walls_are_opaque ? 1 : 0;
+    a.spec_ok = spec_ranges_ok(*p, ctx->walls_are_bounded, ctx->walls_are_opaque) ? 1 : 0;
     ray_range(*p, a.ray_begin, a.ray_end);
 }
 
@@ -454,6 +456,7 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
     ctx->h_walls.assign(segments, segments + n);
     ctx->grid_valid = false;
     ctx->walls_are_opaque = walls_opaque(segments, n);
+    ctx->walls_are_bounded = walls_bounded(segments, n);
     return RAR_OK;
 }
 
@@ -1355,6 +1358,25 @@ int rar_measure_fp32_peak(rar_context *ctx, double *lane_ops_per_s) {
     RAR_CUDA(ctx, e);
     const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
     *lane_ops_per_s = ops / (best_ms * 1e-3);
+    return RAR_OK;
+}
+
+int rar_selftest_arithmetic(rar_context *ctx, int64_t n_samples, uint32_t seed, uint64_t *mismatches) {
+    RAR_ENTER(ctx);
+    if (n_samples < 0 || !mismatches) return fail(ctx, RAR_ERR_INVALID, "bad selftest arguments");
+    DevBuf<unsigned long long> d;
+    RAR_CUDA(ctx, d.reserve(8));
+    cudaError_t e = cudaMemsetAsync(d.p, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess && n_samples > 0) {
+        e = launch_arithmetic_selftest(n_samples, seed, d.p, ctx->dev.sm_count * 8, ctx->stream);
+        ctx->launches++;
+    }
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    d.release();
+    RAR_CUDA(ctx, e);
+    for (int k = 0; k < 5; k++) mismatches[k] = h[k];
     return RAR_OK;
 }
 

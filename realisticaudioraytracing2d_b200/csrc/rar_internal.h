@@ -41,6 +41,7 @@ struct TraceLaunch {
     GridView grid;
     int use_grid;
     int opaque;  // no wall has transmission > 0: kernels without the transmit/refract branch may be used
+    int spec_ok; // opaque, and every operand range the range-checked-once arithmetic assumes holds (spec_ranges_ok)
 };
 
 struct DeviceFacts {
@@ -53,6 +54,7 @@ struct DeviceFacts {
 cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFacts &dev, cudaStream_t stream,
                          int *launches);
 cudaError_t launch_fp32_peak(float *d_sink, int blocks, int threads, int iters, cudaStream_t stream);
+cudaError_t launch_arithmetic_selftest(long long n, uint32_t seed, unsigned long long *d_mism, int blocks, cudaStream_t stream);
 
 // conv_kernels.cu -- all spectra are "packed half spectra" of a real FFT of size 2*B: B complex values
 // per block, bin 0 holding (DC, Nyquist) in (re, im).

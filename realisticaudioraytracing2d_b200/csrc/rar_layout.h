@@ -35,6 +35,28 @@ inline bool walls_opaque(const rar_segment *in, int n) {
     return true;
 }
 
+// Preconditions of the SPEC kernels (rar_math.cuh "*_inrange", rar_ray.cuh): with every wall coordinate finite and
+// at most 2^30 in magnitude, the source inside the same bound, the speed of sound within [2^-20, 2^20] and at most
+// 2^15 bounces, a ray's position stays below 2^43 (each step is shorter than 1e8), so for every filter survivor
+// eps <= |dotP| <= 2^32 and |num1| <= 2^75, and closest / c lies within 2^+-47.
+inline bool walls_bounded(const rar_segment *in, int n) {
+    const float lim = 1073741824.0f;  // 2^30
+    for (int w = 0; w < n; w++) {
+        const float v[4] = {in[w].start[0], in[w].start[1], in[w].end[0], in[w].end[1]};
+        for (float x : v)
+            if (!(std::fabs(x) <= lim)) return false;  // also rejects NaN
+    }
+    return true;
+}
+inline bool spec_ranges_ok(const rar_trace_params &p, bool walls_are_bounded, bool walls_are_opaque) {
+    const float lim = 1073741824.0f;
+    if (!walls_are_bounded || !walls_are_opaque) return false;
+    if (!(std::fabs(p.source_pos[0]) <= lim && std::fabs(p.source_pos[1]) <= lim)) return false;
+    if (!(std::fabs(p.listener_pos[0]) <= lim && std::fabs(p.listener_pos[1]) <= lim)) return false;
+    if (!(p.speed_of_sound >= 9.5367431640625e-07f && p.speed_of_sound <= 1048576.0f)) return false;
+    return p.max_bounce_count <= 32768;
+}
+
 inline RayConsts ray_consts(const rar_trace_params &p) {
     RayConsts c;
     c.source_x = p.source_pos[0];
@@ -51,6 +73,8 @@ inline RayConsts ray_consts(const rar_trace_params &p) {
     c.impulse_length = p.impulse_length;
     c.time_divisor = p.time_divisor;
     c.count_executed = (p.flags & RAR_FLAG_COUNT_EXECUTED) ? 1 : 0;
+    c.sample_rate_f = (float)p.sample_rate;
+    c.impulse_length_f = (float)p.impulse_length;
     return c;
 }
 

@@ -43,7 +43,21 @@ struct RayConsts {
     int sample_rate, impulse_length;
     float time_divisor;
     int count_executed;  // with COUNT: resolve (and count) only the shadow rays the production kernel resolves
+    float sample_rate_f, impulse_length_f;  // (float) of the two integers above, converted once on the host
 };
+
+// SPEC kernels (see Scene::kSpec): the refined reciprocal of the launch-invariant speed of sound, formed once per
+// thread from the MUFU seed, so that x / c is three FMAs (div_with_rcp) instead of the guarded 12-instruction
+// sequence -- bit-identical to __fdiv_rn for the operands the SPEC preconditions admit.
+struct SpecConsts {
+    float c, inv_c;
+};
+RAR_HD SpecConsts spec_consts(const RayConsts &p) {
+    SpecConsts s;
+    s.c = p.speed_of_sound;
+    s.inv_c = rcp_refine(p.speed_of_sound, mufu_rcp(p.speed_of_sound));
+    return s;
+}
 
 struct RayCounters {
     unsigned long long ray_bounces, nearest_tests, shadow_tests, direct_hits, nee_hits;
@@ -91,9 +105,13 @@ RAR_HD void ray_init(RayState<BANDS> &r, uint32_t id, const RayConsts &p, uint32
 // which cannot round down to 1), and fl(num2/dotP) >= 0 <=> num2 is zero or has the sign of dotP (the only
 // other way is a quotient of opposite signs underflowing to -0, |num2/dotP| <= 2^-150, which the filter
 // has already excluded -- see the header comment).
+// SPEC (scene and source coordinates bounded by 2^30, checked by the host): eps <= |dotP| <= 2^40 and
+// |num1| <= 2^63, so the division needs no range guard; a |num1| below 2^-100 yields some quotient below 2^-80,
+// rejected by t1 >= eps exactly like the true quotient.
+template <bool SPEC = false>
 RAR_HD float intersect_exact(float num1, float num2, float dotP) {
     if (fabsf(dotP) < kEps) return kInf;
-    const float t1 = rar_div(num1, dotP);
+    const float t1 = SPEC ? div_inrange(num1, dotP) : rar_div(num1, dotP);
     const bool same_sign = (num2 >= 0.0f) == (dotP >= 0.0f);
     const bool t2_ok = (num2 == 0.0f || same_sign) && fabsf(num2) <= fabsf(dotP);
     return (t1 >= kEps && t2_ok) ? t1 : kInf;
@@ -289,14 +307,14 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
     int w = 0;
 #define RAR_NEAREST_EXACT(T, W)                                      \
     {                                                                \
-        const float d = intersect_exact((T).num1, (T).num2, (T).dotP); \
+        const float d = intersect_exact<Scene::kSpec>((T).num1, (T).num2, (T).dotP); \
         if (d < closest) {                                           \
             closest = d;                                             \
             closest_m = d * kSlack;                                  \
             hit = (W);                                               \
         }                                                            \
     }
-    if (Scene::kPeelFirstBatch && n >= 4) {  // first batch: no bound yet
+    if (Scene::kFixed4 || (Scene::kPeelFirstBatch && n >= 4)) {  // first batch: no bound yet
         const WallTest t0 = wall_test(sc.geo(0), ox, oy, dx, ndy);
         const WallTest t1 = wall_test(sc.geo(1), ox, oy, dx, ndy);
         const WallTest t2 = wall_test(sc.geo(2), ox, oy, dx, ndy);
@@ -311,23 +329,25 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
         }
         w = 4;
     }
-    for (; w + 4 <= n; w += 4) {
-        const WallTest t0 = wall_test(sc.geo(w), ox, oy, dx, ndy);
-        const WallTest t1 = wall_test(sc.geo(w + 1), ox, oy, dx, ndy);
-        const WallTest t2 = wall_test(sc.geo(w + 2), ox, oy, dx, ndy);
-        const WallTest t3 = wall_test(sc.geo(w + 3), ox, oy, dx, ndy);
-        const bool p0 = wall_pass(t0, closest_m), p1 = wall_pass(t1, closest_m);
-        const bool p2 = wall_pass(t2, closest_m), p3 = wall_pass(t3, closest_m);
-        if (p0 | p1 | p2 | p3) {
-            if (p0) RAR_NEAREST_EXACT(t0, w)
-            if (p1) RAR_NEAREST_EXACT(t1, w + 1)
-            if (p2) RAR_NEAREST_EXACT(t2, w + 2)
-            if (p3) RAR_NEAREST_EXACT(t3, w + 3)
+    if constexpr (!Scene::kFixed4) {  // kFixed4: the scene has exactly four walls, the batch above was all of them
+        for (; w + 4 <= n; w += 4) {
+            const WallTest t0 = wall_test(sc.geo(w), ox, oy, dx, ndy);
+            const WallTest t1 = wall_test(sc.geo(w + 1), ox, oy, dx, ndy);
+            const WallTest t2 = wall_test(sc.geo(w + 2), ox, oy, dx, ndy);
+            const WallTest t3 = wall_test(sc.geo(w + 3), ox, oy, dx, ndy);
+            const bool p0 = wall_pass(t0, closest_m), p1 = wall_pass(t1, closest_m);
+            const bool p2 = wall_pass(t2, closest_m), p3 = wall_pass(t3, closest_m);
+            if (p0 | p1 | p2 | p3) {
+                if (p0) RAR_NEAREST_EXACT(t0, w)
+                if (p1) RAR_NEAREST_EXACT(t1, w + 1)
+                if (p2) RAR_NEAREST_EXACT(t2, w + 2)
+                if (p3) RAR_NEAREST_EXACT(t3, w + 3)
+            }
         }
-    }
-    for (; w < n; w++) {
-        const WallTest t = wall_test(sc.geo(w), ox, oy, dx, ndy);
-        if (wall_pass(t, closest_m)) RAR_NEAREST_EXACT(t, w)
+        for (; w < n; w++) {
+            const WallTest t = wall_test(sc.geo(w), ox, oy, dx, ndy);
+            if (wall_pass(t, closest_m)) RAR_NEAREST_EXACT(t, w)
+        }
     }
 #undef RAR_NEAREST_EXACT
     closest_out = closest;
@@ -355,9 +375,10 @@ RAR_HD ShadowRay make_shadow_ray(float sx, float sy, float ex, float ey, float d
 }
 
 // Does wall record s block the shadow ray?  (filter, then the literal formula for survivors)
+template <bool SPEC = false>
 RAR_HD bool shadow_blocked_by(const f4 s, const ShadowRay &q, float lim_m) {
     const WallTest t = wall_test(s, q.sx, q.sy, q.dx, q.ndy);
-    return wall_pass(t, lim_m) && intersect_exact(t.num1, t.num2, t.dotP) < q.lim;
+    return wall_pass(t, lim_m) && intersect_exact<SPEC>(t.num1, t.num2, t.dotP) < q.lim;
 }
 
 // One thread walks all walls with the reference's early exit.  Returns true when visible; *tests receives
@@ -371,6 +392,24 @@ RAR_HD bool check_vis(const Scene &sc, const ShadowRay &q, int *tests) {
         return false;
     }
     const float lim_m = q.lim * kSlack;
+    constexpr bool SP = Scene::kSpec;
+    if constexpr (Scene::kFixed4) {  // exactly four walls: one batch, no loop
+        const WallTest t0 = wall_test(sc.geo(0), q.sx, q.sy, q.dx, q.ndy);
+        const WallTest t1 = wall_test(sc.geo(1), q.sx, q.sy, q.dx, q.ndy);
+        const WallTest t2 = wall_test(sc.geo(2), q.sx, q.sy, q.dx, q.ndy);
+        const WallTest t3 = wall_test(sc.geo(3), q.sx, q.sy, q.dx, q.ndy);
+        const bool p0 = wall_pass(t0, lim_m), p1 = wall_pass(t1, lim_m);
+        const bool p2 = wall_pass(t2, lim_m), p3 = wall_pass(t3, lim_m);
+        int first4 = -1;
+        if (p0 | p1 | p2 | p3) {
+            if (p3 && intersect_exact<SP>(t3.num1, t3.num2, t3.dotP) < q.lim) first4 = 3;
+            if (p2 && intersect_exact<SP>(t2.num1, t2.num2, t2.dotP) < q.lim) first4 = 2;
+            if (p1 && intersect_exact<SP>(t1.num1, t1.num2, t1.dotP) < q.lim) first4 = 1;
+            if (p0 && intersect_exact<SP>(t0.num1, t0.num2, t0.dotP) < q.lim) first4 = 0;
+        }
+        if (tests) *tests = first4 >= 0 ? first4 + 1 : 4;
+        return first4 < 0;
+    }
     int w = 0;
     int first = -1;  // first blocking wall
     for (; w + 4 <= n; w += 4) {
@@ -381,15 +420,15 @@ RAR_HD bool check_vis(const Scene &sc, const ShadowRay &q, int *tests) {
         const bool p0 = wall_pass(t0, lim_m), p1 = wall_pass(t1, lim_m);
         const bool p2 = wall_pass(t2, lim_m), p3 = wall_pass(t3, lim_m);
         if (p0 | p1 | p2 | p3) {
-            if (p0 && intersect_exact(t0.num1, t0.num2, t0.dotP) < q.lim) { first = w; break; }
-            if (p1 && intersect_exact(t1.num1, t1.num2, t1.dotP) < q.lim) { first = w + 1; break; }
-            if (p2 && intersect_exact(t2.num1, t2.num2, t2.dotP) < q.lim) { first = w + 2; break; }
-            if (p3 && intersect_exact(t3.num1, t3.num2, t3.dotP) < q.lim) { first = w + 3; break; }
+            if (p0 && intersect_exact<SP>(t0.num1, t0.num2, t0.dotP) < q.lim) { first = w; break; }
+            if (p1 && intersect_exact<SP>(t1.num1, t1.num2, t1.dotP) < q.lim) { first = w + 1; break; }
+            if (p2 && intersect_exact<SP>(t2.num1, t2.num2, t2.dotP) < q.lim) { first = w + 2; break; }
+            if (p3 && intersect_exact<SP>(t3.num1, t3.num2, t3.dotP) < q.lim) { first = w + 3; break; }
         }
     }
     if (first < 0) {
         for (; w < n; w++) {
-            if (shadow_blocked_by(sc.geo(w), q, lim_m)) { first = w; break; }
+            if (shadow_blocked_by<SP>(sc.geo(w), q, lim_m)) { first = w; break; }
         }
     }
     if (tests) *tests = first >= 0 ? first + 1 : n;
@@ -440,9 +479,10 @@ RAR_HD void bounce_nearest(const Scene &sc, const RayState<BANDS> &r, BounceCtx<
 }
 
 // :74-84: does the ray cross the listener circle at (lx, ly) before the wall?  Uses the state BEFORE the advance.
-template <int BANDS, bool COUNT>
+// SPEC: see bounce_advance.
+template <int BANDS, bool COUNT, bool SPEC = false>
 RAR_HD void listener_direct(const RayConsts &p, float lx, float ly, const RayState<BANDS> &r, float closest,
-                            Arrival<BANDS> &direct, RayCounters *ctr) {
+                            Arrival<BANDS> &direct, RayCounters *ctr, const SpecConsts *sp = nullptr) {
     direct.has = 0;
     if (r.wall_depth != 0) return;
     float dl = intersect_circle(r.px, r.py, r.dx, r.dy, lx, ly, p.listener_radius);
@@ -450,7 +490,7 @@ RAR_HD void listener_direct(const RayConsts &p, float lx, float ly, const RaySta
         direct.has = 1;
         direct.hx = rar_fma(r.dx, dl, r.px);
         direct.hy = rar_fma(r.dy, dl, r.py);
-        direct.t = r.time + rar_div(dl, r.speed);
+        direct.t = r.time + (SPEC ? div_with_rcp(dl, sp->c, sp->inv_c) : rar_div(dl, r.speed));  // eps < dl < 1e8
         float total = r.dist + dl;
         float denom = fmaxf(1.0f, total * total);
         direct.e = rar_div(r.energy, denom);
@@ -463,19 +503,23 @@ RAR_HD void listener_direct(const RayConsts &p, float lx, float ly, const RaySta
 }
 
 // :86-99: end the ray if nothing was hit, else move it to the wall and fetch the wall's material.
-// dbg: where to record this bounce's vertex for the debugRays buffer, or nullptr; dbg_flags bit 0: record
+// dbg: where to record this bounce's vertex for the debugRays buffer (dereferenced only when dbg_flags asks for
+// it); dbg_flags bit 0: record
 // wall hits (:96-97, thread id < 100), bit 1: record the escape vertex (:87-88, thread id < debugRayCount).
+// SPEC (opaque scene, so the ray's speed is the launch-invariant speed of sound, itself within [2^-20, 2^20]):
+// closest lies in [eps, 1e8), so closest / speed needs no range guard and uses the per-thread reciprocal.
 template <int BANDS, class Scene>
-RAR_HD bool bounce_advance(const Scene &sc, RayState<BANDS> &r, BounceCtx<BANDS> &c, f4 *dbg, int dbg_flags) {
+RAR_HD bool bounce_advance(const Scene &sc, RayState<BANDS> &r, BounceCtx<BANDS> &c, f4 *dbg, int dbg_flags,
+                           const SpecConsts *sp = nullptr) {
     if (c.hit < 0) {  // :86-90
-        if (dbg && (dbg_flags & 2)) *dbg = f4{rar_fma(r.dx, 20.0f, r.px), rar_fma(r.dy, 20.0f, r.py), 0.0f, 0.0f};
+        if (dbg_flags & 2) *dbg = f4{rar_fma(r.dx, 20.0f, r.px), rar_fma(r.dy, 20.0f, r.py), 0.0f, 0.0f};
         return false;
     }
     r.px = rar_fma(r.dx, c.closest, r.px);  // :92-94
     r.py = rar_fma(r.dy, c.closest, r.py);
-    r.time += rar_div(c.closest, r.speed);
+    r.time += Scene::kSpec ? div_with_rcp(c.closest, sp->c, sp->inv_c) : rar_div(c.closest, r.speed);
     r.dist += c.closest;
-    if (dbg && (dbg_flags & 1)) *dbg = f4{r.px, r.py, r.energy, 0.0f};  // :96-97
+    if (dbg_flags & 1) *dbg = f4{r.px, r.py, r.energy, 0.0f};  // :96-97
 
     c.m0 = sc.mat0(c.hit);  // :99
     c.m1 = sc.mat1(c.hit);
@@ -494,8 +538,10 @@ RAR_HD bool bounce_advance(const Scene &sc, RayState<BANDS> &r, BounceCtx<BANDS>
 // threshold (:111); checkVis has no side effect, so the contribution is computed first and the shadow ray
 // is requested only when the outcome can matter (with COUNT in reference mode it is always requested, so
 // that the test counters are the reference's).
-template <int BANDS, bool COUNT>
-RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<BANDS> &r, BounceCtx<BANDS> &c) {
+template <int BANDS, bool COUNT, bool SPEC = false>
+RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<BANDS> &r, BounceCtx<BANDS> &c,
+                         const SpecConsts *sp = nullptr) {
+    static_assert(!(SPEC && COUNT), "the SPEC pieces exist for the production kernels only");
     c.want_shadow = 0;
     c.nee_candidate = 0;
     if (r.wall_depth != 0) return;
@@ -510,9 +556,34 @@ RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<
         if (ek <= 0.0f || (ek * ek) * dot2(wnx, wny, wnx, wny) < (0.96e-10f * d2) * d2) return;
     }
     const float tlx = lx - r.px, tly = ly - r.py;
-    const float dl = rar_sqrt(dot2(tlx, tly, tlx, tly));
+    const float dl2 = dot2(tlx, tly, tlx, tly);
     const bool flip = c.dir_dot_n > 0.0f;
     const float enx = flip ? -wnx : wnx, eny = flip ? -wny : wny;
+    if (SPEC && __builtin_expect(in_safe_range(dl2), 1)) {
+        // One range test for the whole estimate: 2^-100 <= dl^2 <= 2^100 puts dl and 1/dl within 2^+-50, and with
+        // 0 <= dist < 2^34 (a sum of at most 2^15 distances below 1e8) total^2 within [2^-100, 2^69]; every
+        // operation below is then the fast path of its correctly rounded intrinsic, bit for bit.
+        const float dl = sqrt_inrange(dl2);
+        const float inv_dl = rcp_inrange(dl);
+        const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
+        const float total = r.dist + dl;
+        c.geo = cos_t * 0.5f;
+        c.inv = rcp_inrange(total * total);
+        c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
+        c.nee_candidate = c.nee_e > 1e-5f;
+        c.want_shadow = c.nee_candidate;
+        if (c.want_shadow) {
+            const float sx = rar_fma(wnx, kEps, r.px), sy = rar_fma(wny, kEps, r.py);
+            c.shadow.sx = sx;  // make_shadow_ray with the reciprocal already at hand
+            c.shadow.sy = sy;
+            c.shadow.dx = (lx - sx) * inv_dl;
+            c.shadow.ndy = -((ly - sy) * inv_dl);
+            c.shadow.lim = dl - 0.1f;
+            c.nee_t = r.time + div_with_rcp(dl, sp->c, sp->inv_c);
+        }
+        return;
+    }
+    const float dl = rar_sqrt(dl2);
     const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
     const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
     const float total = r.dist + dl;
@@ -551,8 +622,10 @@ RAR_HD void nee_arrival(const RayState<BANDS> &r, const BounceCtx<BANDS> &c, boo
 // is then false for every draw (random() >= 0), so the whole transmit/refract branch is compiled out -- the draw
 // itself still happens.  Scenes of opaque walls are the common case and the kernel is a third smaller without
 // that branch (config 2: 0.607 -> 0.56 ms).
-template <int BANDS, bool OPAQUE = false>
+// SPEC: one range test on |m|^2 covers the square root and the reciprocal of the final normalisation.
+template <int BANDS, bool OPAQUE = false, bool SPEC = false>
 RAR_HD bool bounce_scatter(const RayConsts &p, RayState<BANDS> &r, const BounceCtx<BANDS> &c) {
+    static_assert(!SPEC || OPAQUE, "SPEC needs the ray's speed to be launch-invariant: opaque scenes only");
     r.energy *= c.keep;  // :121-122
     if (BANDS > 1) {
 #pragma unroll
@@ -615,7 +688,8 @@ RAR_HD bool bounce_scatter(const RayConsts &p, RayState<BANDS> &r, const BounceC
         mx = rar_fma(c.m0.w, dfx - spx, spx);
         my = rar_fma(c.m0.w, dfy - spy, spy);
     }
-    const float inv = rar_rcp(rar_sqrt(dot2(mx, my, mx, my)));
+    const float m2 = dot2(mx, my, mx, my);
+    const float inv = (SPEC && __builtin_expect(in_safe_range(m2), 1)) ? rcp_inrange(sqrt_inrange(m2)) : rar_rcp(rar_sqrt(m2));
     r.dx = mx * inv;
     r.dy = my * inv;
     r.px = rar_fma(nx, kEps, r.px);
@@ -627,13 +701,14 @@ RAR_HD bool bounce_scatter(const RayConsts &p, RayState<BANDS> &r, const BounceC
 // Returns false when the ray ended without hitting a wall (:86-90).
 template <int BANDS, bool COUNT, class Scene>
 RAR_HD bool bounce_begin(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
-                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
+                         BounceCtx<BANDS> &c, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0,
+                         const SpecConsts *sp = nullptr) {
     c.want_shadow = 0;
     c.nee_candidate = 0;
     bounce_nearest<BANDS, COUNT>(sc, r, c, ctr);
-    listener_direct<BANDS, COUNT>(p, p.listener_x, p.listener_y, r, c.closest, direct, ctr);
-    if (!bounce_advance(sc, r, c, dbg, dbg_flags)) return false;
-    listener_nee<BANDS, COUNT>(p, p.listener_x, p.listener_y, r, c);
+    listener_direct<BANDS, COUNT, Scene::kSpec>(p, p.listener_x, p.listener_y, r, c.closest, direct, ctr, sp);
+    if (!bounce_advance(sc, r, c, dbg, dbg_flags, sp)) return false;
+    listener_nee<BANDS, COUNT, Scene::kSpec>(p, p.listener_x, p.listener_y, r, c, sp);
     return true;
 }
 
@@ -644,16 +719,17 @@ RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &
                           const BounceCtx<BANDS> &c, bool visible, RayCounters *ctr) {
     (void)sc;
     nee_arrival<BANDS, COUNT>(r, c, visible, nee, ctr);
-    return bounce_scatter<BANDS, OPAQUE>(p, r, c);
+    return bounce_scatter<BANDS, OPAQUE, Scene::kSpec>(p, r, c);
 }
 
 // The three phases with a per-thread shadow walk: what a single thread of the reference does.
 template <int BANDS, bool COUNT, bool OPAQUE = false, class Scene>
 RAR_HD bool ray_bounce(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &direct,
-                       Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0) {
+                       Arrival<BANDS> &nee, RayCounters *ctr, f4 *dbg = nullptr, int dbg_flags = 0,
+                       const SpecConsts *sp = nullptr) {
     BounceCtx<BANDS> c;
     nee.has = 0;
-    if (!bounce_begin<BANDS, COUNT>(sc, p, r, direct, c, ctr, dbg, dbg_flags)) return false;
+    if (!bounce_begin<BANDS, COUNT>(sc, p, r, direct, c, ctr, dbg, dbg_flags, sp)) return false;
     bool visible = true;
     if (c.want_shadow) {
         int tests = 0;

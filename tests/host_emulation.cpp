@@ -9,10 +9,12 @@
 #include "../realisticaudioraytracing2d_b200/csrc/rar_layout.h"
 
 namespace {
-template <bool GRID>
+template <bool GRID, int FAST = 0>
 struct HostSceneT {
     static constexpr bool kGrid = GRID;
     static constexpr bool kPeelFirstBatch = !GRID;  // exercise the small-scene filter of the nearest-hit scan
+    static constexpr bool kSpec = (FAST & 1) != 0;   // the range-checked-once pieces (on the host: plain IEEE ops)
+    static constexpr bool kFixed4 = (FAST & 2) != 0; // exactly four walls, no loops
     rar::GridView gv;
     const rar::GridView &grid() const { return gv; }
     rar::f4 grid_geo(uint32_t i) const { return gv.item_geo[i]; }
@@ -34,6 +36,7 @@ template <int BANDS, bool COUNT, bool OPAQUE, class SceneT>
 void run(const SceneT &sc, const rar_trace_params &p, long long *hist, Hit *hits, long long cap, long long *count,
          rar::RayCounters &ctr) {
     rar::RayConsts c = rar::ray_consts(p);
+    const rar::SpecConsts spc = rar::spec_consts(c);
     long long lo, hi;
     rar::ray_range(p, lo, hi);
     for (long long id = lo; id < hi; id++) {
@@ -41,7 +44,7 @@ void run(const SceneT &sc, const rar_trace_params &p, long long *hist, Hit *hits
         rar::ray_init(r, (uint32_t)id, c);
         for (int i = 0; i < c.max_bounce_count; i++) {
             rar::Arrival<BANDS> a[2];
-            bool alive = rar::ray_bounce<BANDS, COUNT, OPAQUE>(sc, c, r, a[0], a[1], &ctr);
+            bool alive = rar::ray_bounce<BANDS, COUNT, OPAQUE>(sc, c, r, a[0], a[1], &ctr, nullptr, 0, SceneT::kSpec ? &spc : nullptr);
             for (int k = 0; k < 2; k++) {
                 if (!a[k].has) continue;
                 if (hits) {
@@ -87,6 +90,22 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
     }
     HostScene sc;
     sc.g = g.data(); sc.m0 = m0.data(); sc.m1 = m1.data(); sc.ba = band_abs; sc.n = n; sc.nb = p->bands;
+    // the launch code's choice of the range-checked-once (SPEC) and four-wall (FIXED4) production instantiations
+    if (!counting && (p->bands <= 1 || p->bands == 8) && rar::spec_ranges_ok(*p, rar::walls_bounded(walls, n), opaque)) {
+        HostSceneT<false, 1> s1;
+        s1.g = sc.g; s1.m0 = sc.m0; s1.m1 = sc.m1; s1.ba = sc.ba; s1.n = n; s1.nb = sc.nb;
+        HostSceneT<false, 3> s3;
+        s3.g = sc.g; s3.m0 = sc.m0; s3.m1 = sc.m1; s3.ba = sc.ba; s3.n = n; s3.nb = sc.nb;
+        if (p->bands <= 1) {
+            if (n == 4) run<1, false, true>(s3, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+            else run<1, false, true>(s1, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        } else {
+            if (n == 4) run<8, false, true>(s3, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+            else run<8, false, true>(s1, *p, hist, (Hit *)hits, cap, &cnt, ctr);
+        }
+        if (count) *count = cnt;
+        return 0;
+    }
     if (p->bands <= 1) {
         if (counting) run<1, true, false>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);
         else if (opaque) run<1, false, true>(sc, *p, hist, (Hit *)hits, cap, &cnt, ctr);

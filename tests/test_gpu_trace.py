@@ -430,12 +430,21 @@ def test_arbitrary_band_counts_are_traced_in_chunks_of_eight(ctx, oracle, bands)
     assert np.array_equal(ctx.ir_read_fixed(0, 6000 * bands), want.hist)
 
 
-@pytest.mark.parametrize("case", ["shoebox_diffuse", "maze600", "maze600_b8", "maze600_grid"])
+@pytest.mark.parametrize("case", ["shoebox_diffuse", "maze600", "maze600_b8", "maze600_grid", "maze120", "maze120_b8",
+                                  "shoebox_b8"])
 def test_production_kernels_for_opaque_scenes(ctx, oracle, case):
     """Scenes without any transmitting wall run kernels compiled without the transmit/refract branch (production
-    mode only: no counters).  They must reproduce the oracle, which always evaluates `rngVal < transmission`."""
+    mode only: no counters).  They must reproduce the oracle, which always evaluates `rngVal < transmission`.
+    shoebox*: the four-wall, range-checked-once instantiation (FAST 3); maze120*: range-checked-once, general wall
+    count (FAST 1); maze600*: cooperative / grid kernels."""
     if case == "shoebox_diffuse":
         sc, bands, flags = scenes.shoebox(ray_count=100_000, max_bounces=24, scattering=0.4), 1, 0
+    elif case == "shoebox_b8":
+        sc, bands, flags = scenes.shoebox(ray_count=50_000, max_bounces=24, scattering=0.2), 8, 0
+        sc.band_absorption = np.random.default_rng(5).uniform(0.02, 0.3, size=(4, 8)).astype(np.float32)
+    elif case.startswith("maze120"):
+        sc = scenes.maze(n_segments=120, ray_count=30_000, max_bounces=24, bands=8, seed=3)
+        bands, flags = (8 if case.endswith("_b8") else 1), 0
     else:
         sc = scenes.maze(n_segments=600, ray_count=30_000, max_bounces=16, bands=8, seed=11)
         bands = 8 if case == "maze600_b8" else 1
@@ -451,6 +460,54 @@ def test_production_kernels_for_opaque_scenes(ctx, oracle, case):
     want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, dict(kw, flags=0)),
                         band_abs=sc.band_absorption if bands > 1 else None).hist
     assert np.array_equal(ctx.ir_read_fixed(0, n * bands), want) and np.count_nonzero(want) > 500
+
+
+def test_arithmetic_selftest(ctx):
+    """The range-checked-once forms of 1/x, sqrt(x), a/b (csrc/rar_math.cuh) equal the correctly rounded intrinsics
+    bit for bit over the admitted operand ranges (2^27 operand sets per seed)."""
+    for seed in (1, 2):
+        assert ctx.selftest_arithmetic(1 << 27, seed) == [0, 0, 0, 0, 0]
+
+
+def test_fast_and_guarded_kernels_agree(ctx, oracle, monkeypatch):
+    """RAR_NO_FAST=1 selects the kernels with a guard around every division / square root; same histogram."""
+    for sc in (scenes.shoebox(ray_count=300_000, max_bounces=32), scenes.maze(n_segments=90, ray_count=50_000, max_bounces=20, bands=1, seed=9)):
+        kw = trace_kwargs(sc)
+        n = kw["impulse_length"]
+        ctx.set_walls(sc.walls)
+        out = []
+        for no_fast in ("0", "1"):
+            monkeypatch.setenv("RAR_NO_FAST", no_fast)
+            ctx.ir_clear(0, n, 1)
+            ctx.trace(capi_params(_capi, kw), 0)
+            out.append(ctx.ir_read_fixed(0, n))
+        monkeypatch.delenv("RAR_NO_FAST")
+        assert np.array_equal(out[0], out[1]) and np.count_nonzero(out[0]) > 1000
+
+
+def test_degenerate_inputs_opaque_scene(ctx, oracle):
+    """The degenerate placements of test_degenerate_inputs_match_the_oracle in an OPAQUE four-wall room, i.e. through
+    the range-checked-once kernels: a zero distance to the listener, a source on a corner, out-of-range speed and
+    coordinates (which must select the guarded kernels), a huge gain."""
+    base = scenes.shoebox(ray_count=4096, max_bounces=16, scattering=0.3)
+    far = scenes.shoebox(width=3e9, height=2e9, ray_count=4096, max_bounces=8)     # coordinates beyond 2^30
+    cases = [
+        (base, dict(listener=(10.0, 3.0))),                   # listener centre ON a wall: a hit point can coincide with it
+        (base, dict(source=(0.0, 0.0))),                      # source on a corner
+        (base, dict(source=(5.0, 3.0), listener=(5.0, 3.0))),
+        (base, dict(listener_radius=1e-3)),
+        (base, dict(input_gain=1e9)),
+        (base, dict(speed_of_sound=1e-7)),                    # below the range the reciprocal trick admits
+        (base, dict(speed_of_sound=3e6)),
+        (far, dict(source=(1e9, 1e9), listener=(2e9, 1.5e9), speed_of_sound=3e8)),
+    ]
+    for i, (sc, over) in enumerate(cases):
+        kw = trace_kwargs(sc, **over)
+        want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw)).hist
+        ctx.set_walls(sc.walls)
+        ctx.ir_clear(0, kw["impulse_length"], 1)
+        ctx.trace(capi_params(_capi, kw), 0)
+        assert np.array_equal(ctx.ir_read_fixed(0, kw["impulse_length"]), want), i
 
 
 def test_asynchronous_ir_readback(ctx, oracle):
