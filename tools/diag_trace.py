@@ -1,5 +1,7 @@
+"""Bisects a histogram mismatch: per-ray-range bounce counters, hit lists and histograms of the GPU kernels against the
+CPU oracle on the config-2 shoebox (written while chasing a ptxas miscompile of a predicate-derived shared address)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from oracle import oracle as O
 from realisticaudioraytracing2d_b200 import _capi, scenes
