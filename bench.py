@@ -402,6 +402,10 @@ def run_ours(args):
     except Exception as ex:
         extra["conv"] = {"error": str(ex)}
     try:
+        extra["banded"] = bench_banded(env, peaks, peaks_kind)
+    except Exception as ex:
+        extra["banded"] = {"error": str(ex)}
+    try:
         extra["clip_prep"] = bench_clip_prep(ctx, _capi, torch, stream, dev, peaks, peaks_kind)
     except Exception as ex:
         extra["clip_prep"] = {"error": str(ex)}
@@ -618,7 +622,8 @@ def bench_listeners(env):
     n = sc.impulse_length
     gx, gy = np.meshgrid(np.linspace(8, 92, 32), np.linspace(8, 92, 32))
     grid = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.float32)
-    mine = grid[(per_gpu * rank) % 1024:(per_gpu * rank) % 1024 + per_gpu]
+    start = (256 + per_gpu * rank) % 1024          # rank 0 takes grid rows 8-11, the ones around the source
+    mine = grid[start:start + per_gpu]
     ctx.set_walls(sc.walls)
 
     def clear():
@@ -638,10 +643,18 @@ def bench_listeners(env):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    h0 = ctx.ir_read_fixed(first, n)
-    ctx.ir_clear(first + per_gpu, n, 1)                        # listener 0 again as a plain single-listener trace
-    ctx.trace(prm(listener=(float(mine[0, 0]), float(mine[0, 1]))), first + per_gpu)
-    same = bool(np.array_equal(ctx.ir_read_fixed(first + per_gpu, n), h0)) and bool(h0.any())
+    # the busiest listener again as a plain single-listener trace: identical histogram (most listeners of the maze
+    # hear nothing within 5 bounces)
+    heads = [ctx.ir_read_fixed(first + l, n) for l in range(per_gpu)]
+    k = int(np.argmax([np.count_nonzero(h) for h in heads]))
+    reached = int(sum(1 for h in heads if h.any()))
+    ctx.ir_clear(first + per_gpu, n, 1)
+    ctx.trace(prm(listener=(float(mine[k, 0]), float(mine[k, 1]))), first + per_gpu)
+    single = ctx.ir_read_fixed(first + per_gpu, n)
+    same = bool(np.array_equal(single, heads[k])) and bool(heads[k].any())
+    if not same:
+        sys.stderr.write(f"[bench] listeners: listener {k} fused nonzero {np.count_nonzero(heads[k])} sum {int(heads[k].sum())}; "
+                         f"single nonzero {np.count_nonzero(single)} sum {int(single.sum())}\n")
     clear()
     ctx.get_counters(reset=True)
     ctx.trace_listeners(prm(capi.RAR_FLAG_COUNT_TESTS | capi.RAR_FLAG_COUNT_EXECUTED), mine, first)
@@ -653,7 +666,7 @@ def bench_listeners(env):
                        f"{n} bins per listener, fused listener kernel (each ray traced once per launch)",
            "n_gpus": world, "listeners_total": per_gpu * world, "ms": ms, "ms_per_listener": ms / per_gpu,
            "tests_executed": executed_all, "tests_executed_per_s": executed_all / (ms * 1e-3),
-           "fused_equals_single_listener_trace": _all_true(env, same)}
+           "listeners_with_arrivals_rank0": reached, "fused_equals_single_listener_trace": _all_true(env, same)}
     if env["fp32_peak"]:
         ach = executed * FLOPS_PER_TEST / (ms * 1e-3) / 1e12
         res["roofline"] = {"bound": "fp32-issue", "achieved": ach, "peak": env["fp32_peak"] / 1e12, "unit": "Tlaneop/s",
@@ -792,6 +805,50 @@ def bench_config1(ctx, _capi, scenes, torch, stream):
             "clip_convolve_e2e_ms": clip_ms, "clip_samples_per_s": (len(clip) + n) / (clip_ms * 1e-3)}
 
 
+def bench_banded(env, peaks, peaks_kind):
+    """banded responses into the streaming convolver.  16 streams, each taking its response from its own
+    banded slot of 480 000 bins x 8 bands (a 10 s IR per band, 30.7 MB of Q23.40 words per slot, 491 MB in all, > L2):
+    filter-bank synthesis (band_synth_kernel) followed by the partition spectra (ir_spectra_kernel), per stream."""
+    ctx, capi, scenes, torch, stream = env["ctx"], env["capi"], env["scenes"], env["torch"], env["stream"]
+    S, n, bands, first = 16, 480000, 8, 300
+    cv = capi.Convolver(ctx, S, 256, n)
+    t = np.arange(n, dtype=np.float32) / np.float32(48000)
+    for st in range(S):
+        base = np.abs(scenes.decaying_noise_ir(n, seed=40 + st, decay_s=3.0))
+        ir = base[:, None] * np.exp(-t[:, None] * np.arange(bands, dtype=np.float32)[None, :] * np.float32(0.4))
+        ctx.ir_write(first + st, ir.astype(np.float32).ravel(), bands=bands)
+    slots, ones = np.arange(first, first + S, dtype=np.int32), np.ones(S, dtype=np.int32)
+    cv.set_irs_from_slots(0, slots, ones)                 # builds the band filters, first launches
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        cv.set_irs_from_slots(0, slots, ones)             # one synthesis launch + one spectra launch for the 16 streams
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # a unit impulse into stream 3 must come back as the first block of that slot's synthesised response
+    x = np.zeros((S, 256), np.float32)
+    x[3, 0] = 1.0
+    y = cv.process(x)
+    want = ctx.synthesize_ir(first + 3, 256)
+    err = float(np.linalg.norm(y[3] - want) / max(np.linalg.norm(want), 1e-30))
+    cv.destroy()
+    n_part = (n + 255) // 256
+    nbytes = S * (n * bands * 8 + 2 * n * 4 + n_part * 2048)      # histogram read, response write + read, spectra write
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"workload": f"{S} banded slots x {n} bins x {bands} bands -> filter-bank synthesis -> partition spectra of {S} streams",
+            "ms": ms, "ms_per_stream": ms / S, "responses_per_s": S / (ms * 1e-3), "impulse_check_rel_l2": err,
+            "gpu_launches_per_step": 2,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": _traffic("band_synth_kernel"), "kernel": "band_synth_kernel", "peak_kind": peaks_kind,
+                         "algorithmic_bytes_per_launch": S * (n * bands * 8 + n * 4),
+                         "note": "bytes of the whole step (response clear, synthesis, spectra) over its time; the synthesis "
+                                 "kernel reads the 8-byte histogram words once and adds into the 4-byte response"}}
+
+
 def bench_clip_prep(ctx, _capi, torch, stream, dev, peaks, peaks_kind):
     """LoadSample (mono mix + linear resample) for a batch of clips resident in HBM.
     256 stereo clips of 10 s at 44.1 kHz -> mono 48 kHz; working set 1.39 GB (> L2)."""
@@ -827,9 +884,13 @@ def bench_conv(ctx, _capi, scenes, torch, stream, dev, peaks, peaks_kind, args, 
     S, B, n_ir = 256, 256, 480000
     cv = _capi.Convolver(ctx, S, B, n_ir)
     base = [scenes.decaying_noise_ir(n_ir, seed=100 + k, decay_s=3.0) for k in range(8)]
-    for s in range(S):
-        cv.set_ir(s, np.roll(base[s % 8], s // 8))      # 256 distinct IRs from 8 seeded ones
+    irs = np.stack([np.roll(base[s % 8], s // 8) for s in range(S)])      # 256 distinct IRs from 8 seeded ones
+    t0 = time.perf_counter()
+    cv.set_irs(0, irs)                                   # one call: pinned staging in halves, no stream synchronisation
+    load_call_ms = (time.perf_counter() - t0) * 1e3
     ctx.sync()
+    load_ms = (time.perf_counter() - t0) * 1e3
+    del irs
     g = torch.Generator(device="cpu").manual_seed(1)
     x_host = (torch.rand((S, B), generator=g) * 2 - 1).pin_memory()
     y_host = torch.empty((S, B)).pin_memory()
@@ -865,6 +926,7 @@ def bench_conv(ctx, _capi, scenes, torch, stream, dev, peaks, peaks_kind, args, 
         "samples_per_s": sps, "ms_per_block": ms, "realtime_48k_streams": sps / 48000.0,
         "e2e_samples_per_s": S * B * world / (e2e_ms * 1e-3), "e2e_ms_per_block": e2e_ms,
         "h2d_bytes_per_step": S * B * 4, "d2h_bytes_per_step": S * B * 4, "gpu_launches_per_step": 3,
+        "load_256_responses_ms": load_ms, "load_256_responses_call_returns_after_ms": load_call_ms,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                      "traffic": _traffic("stream_cmac_kernel"), "kernel": "stream_cmac_kernel", "peak_kind": peaks_kind,
                      "algorithmic_bytes_per_launch": bytes_per_block},

@@ -84,6 +84,10 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_get_counters(IntPtr ctx, out RarCounters c, int reset);
         [DllImport(Lib)] public static extern int rar_get_debug_rays(IntPtr ctx, [Out] UnityEngine.Vector4[] dst, long nFloat4);
 
+        // banded model: filter-bank synthesis of a banded slot (RayTraceManagerComplex's WindowSize layout)
+        [DllImport(Lib)] public static extern int rar_set_band_edges(IntPtr ctx, [In] float[] edgesHz, int bands, int sampleRate);
+        [DllImport(Lib)] public static extern int rar_synthesize_ir(IntPtr ctx, int slot, [Out] float[] dst, long n);
+
         [DllImport(Lib)] public static extern int rar_convolve(IntPtr ctx, int slot, [In] float[] input, int inLen, int accumCount, [Out] float[] output, int outLen);
         [DllImport(Lib)] public static extern int rar_convolve_begin(IntPtr ctx, int slot, [In] float[] input, int inLen, int accumCount, out int ticket);
         [DllImport(Lib)] public static extern int rar_poll(IntPtr ctx, int ticket);
@@ -93,6 +97,8 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_conv_destroy(IntPtr conv);
         [DllImport(Lib)] public static extern int rar_conv_set_ir(IntPtr conv, int stream, [In] float[] ir, int irLen, float scale);
         [DllImport(Lib)] public static extern int rar_conv_set_ir_from_slot(IntPtr conv, int stream, int slot, int accumCount);
+        [DllImport(Lib)] public static extern int rar_conv_set_irs(IntPtr conv, int firstStream, int n, [In] float[] irs, int irLen, long irStride, float scale);
+        [DllImport(Lib)] public static extern int rar_conv_set_irs_from_slots(IntPtr conv, int firstStream, int n, [In] int[] slots, [In] int[] accumCounts);
         [DllImport(Lib)] public static extern int rar_conv_update_ir(IntPtr conv, int stream, [In] float[] ir, int irLen, float scale);
         [DllImport(Lib)] public static extern int rar_conv_update_ir_from_slot(IntPtr conv, int stream, int slot, int accumCount);
         [DllImport(Lib)] public static extern int rar_conv_reset(IntPtr conv);

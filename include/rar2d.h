@@ -285,11 +285,29 @@ RAR_API int rar_get_counters(rar_context *ctx, rar_counters *out, int32_t reset)
  * vertex, max(100, debug_ray_count) * (max_bounce_count+1) entries.  Blocking. */
 RAR_API int rar_get_debug_rays(rar_context *ctx, float *out_xyzw, int64_t n_float4);
 
+/* ---- banded model: filter-bank synthesis ------------------------------------------------
+ *
+ * A banded slot (RaytraceOcclusion2D.compute:241-248: IR[bin*WindowSize + band], WindowSize set at
+ * RayTraceManagerComplex.cs:27-28,75-77) holds one energy response per frequency band.  Every convolution entry
+ * point below accepts such a slot and convolves with its broadband synthesis
+ *     h[n] = sum_b (g_b * h_b)[n + 127],   h_b[n] = IR[(n / W) * bands + b] when W divides n, else 0,
+ * W = the (integer) time_divisor the slot was traced with, g_b = the 255-tap linear-phase windowed-sinc band-pass
+ * filter of band b (the filters of contiguous bands sum to a unit impulse, so equal bands synthesise to their common
+ * response exactly).  The response then has impulse_length * W samples.  The reference never finished this stage
+ * (its FFT/IFFT kernels, RaytraceOcclusion2D.compute:352-425, are not dispatched), so these semantics are this
+ * build's; the oracle restates them in direct form.
+ *
+ * rar_set_band_edges: band b covers [edges_hz[b], edges_hz[b+1]); bands+1 ascending values from 0 to sample_rate/2.
+ * NULL restores the default, `bands` equal-width bands -- the linear frequency index of the reference's layout.
+ * rar_synthesize_ir: the synthesised response of a slot (un-normalised, like rar_ir_read), n floats.  Blocking. */
+RAR_API int rar_set_band_edges(rar_context *ctx, const float *edges_hz, int32_t bands, int32_t sample_rate);
+RAR_API int rar_synthesize_ir(rar_context *ctx, int32_t slot, float *out, int64_t n);
+
 /* ---- convolution ------------------------------------------------------------------------------- */
 
 /* RayTraceManager.cs:91-123 ProcessChunk and RayTraceManagerComplex.cs:170-227 BakeAudio: the
- * AudioConvolve kernel (AudioConvolve.compute:13-31) on `in` and the IR in `slot` (band 0 of a
- * banded slot is not supported here: bands must be 1):
+ * AudioConvolve kernel (AudioConvolve.compute:13-31) on `in` and the IR in `slot` (a banded slot
+ * stands for its filter-bank synthesis, see above; ir_len is then impulse_length * time_divisor):
  *   out[n] = (1/accum_count) * sum_k in[k]*ir[n-k] over |in[k]| > 1e-4,  n in [0, in_len+ir_len),
  *   all zeros when accum_count <= 0.
  * Computed as a uniformly partitioned overlap-save FFT convolution (block 256).
@@ -318,8 +336,18 @@ RAR_API int rar_conv_create(rar_context *ctx, int32_t n_streams, int32_t block, 
 RAR_API int rar_conv_destroy(rar_convolver *conv);
 /* IR of one stream from host memory; values are multiplied by `scale` (1/accumCount). */
 RAR_API int rar_conv_set_ir(rar_convolver *conv, int32_t stream, const float *ir, int32_t ir_len, float scale);
-/* IR of one stream taken on the device from a traced slot (bands == 1), scaled by 1/accum_count. */
+/* IR of one stream taken on the device from a traced slot (banded slots through their filter-bank synthesis),
+ * scaled by 1/accum_count. */
 RAR_API int rar_conv_set_ir_from_slot(rar_convolver *conv, int32_t stream, int32_t slot, int32_t accum_count);
+/* The responses of n consecutive streams in one call: irs[k * ir_stride ...] for stream first_stream + k, or slots[k]
+ * scaled by 1 / accum_counts[k] (the slots of one call must have the same shape; banded slots through their
+ * filter-bank synthesis).  Asynchronous: the host arrays are copied during the call through alternating pinned
+ * staging buffers, and nothing waits for the stream -- loading the 256 responses of BASELINE config 5 this way does
+ * not stall the caller the way 256 rar_conv_set_ir calls do. */
+RAR_API int rar_conv_set_irs(rar_convolver *conv, int32_t first_stream, int32_t n, const float *irs, int32_t ir_len,
+                             int64_t ir_stride, float scale);
+RAR_API int rar_conv_set_irs_from_slots(rar_convolver *conv, int32_t first_stream, int32_t n, const int32_t *slots,
+                                        const int32_t *accum_counts);
 /* Time-varying impulse responses (the ping/pong IR of the streaming path, RayTraceManager.cs:64-123,
  * inside the partitioned convolver instead of one full convolution per chunk).  Like rar_conv_set_ir /
  * rar_conv_set_ir_from_slot, but the new response takes effect with a cross-fade over the next block that

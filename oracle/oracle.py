@@ -88,6 +88,10 @@ def lib() -> C.CDLL:
         L.orc_convolve.argtypes = [C.c_void_p, i32, C.c_void_p, i32, i32, C.c_void_p, C.c_int]
         L.orc_convolve_f64.restype = None
         L.orc_convolve_f64.argtypes = [C.c_void_p, i32, C.c_void_p, i32, i32, C.c_void_p, C.c_int]
+        L.orc_band_filter_taps.restype = None
+        L.orc_band_filter_taps.argtypes = [C.c_double, C.c_double, C.c_void_p]
+        L.orc_synthesize_ir.restype = None
+        L.orc_synthesize_ir.argtypes = [C.c_void_p, i32, i32, i32, C.c_void_p, C.c_void_p]
         L.orc_load_sample.restype = i64
         L.orc_load_sample.argtypes = [C.c_void_p, i64, i32, i32, i32, C.c_void_p]
         L.orc_add_loop.restype = C.c_int
@@ -182,6 +186,24 @@ def convolve(inp: np.ndarray, ir: np.ndarray, accum_count: int, n_threads: int =
     out = np.empty(len(inp) + len(ir), dtype=np.float64 if f64 else np.float32)
     fn = lib().orc_convolve_f64 if f64 else lib().orc_convolve
     fn(inp.ctypes.data, len(inp), ir.ctypes.data, len(ir), accum_count, out.ctypes.data, n_threads)
+    return out
+
+
+def band_filter_taps(lo: float, hi: float) -> np.ndarray:
+    """The 255 taps of the band-pass filter of a band with edges lo, hi (fractions of Nyquist)."""
+    g = np.zeros(255, dtype=np.float32)
+    lib().orc_band_filter_taps(lo, hi, g.ctypes.data)
+    return g
+
+
+def synthesize_ir(hist: np.ndarray, bins: int, bands: int, stride: int = 1, edges=None) -> np.ndarray:
+    """Filter-bank synthesis of a banded histogram [bins][bands] in direct form (this build's banded model)."""
+    hist = np.ascontiguousarray(hist, dtype=np.int64)
+    assert hist.size == bins * bands
+    e = None if edges is None else np.ascontiguousarray(edges, dtype=np.float32)
+    assert e is None or len(e) == bands + 1
+    out = np.zeros(bins * stride, dtype=np.float32)
+    lib().orc_synthesize_ir(hist.ctypes.data, bins, bands, stride, e.ctypes.data if e is not None else None, out.ctypes.data)
     return out
 
 

@@ -448,6 +448,48 @@ ORC_API void orc_convolve(const float *in, int32_t input_length, const float *ir
     }
 }
 
+/* ---- banded model: filter-bank synthesis (direct form) --------------------------------------------------------
+ *
+ * The reference's banded variant stops at the banded histogram IR[bin*WindowSize + band]
+ * (RaytraceOcclusion2D.compute:241-248); its FFT/IFFT kernels (:352-425) are never dispatched and no C# consumes the
+ * bands.  The synthesis below is therefore THIS BUILD's definition (include/rar2d.h, "banded model"), restated here
+ * in direct form as the checker of the GPU's frequency-domain overlap-add:
+ *   g_b[n] = w[n] (hi sinc(hi m) - lo sinc(lo m)),  m = n - 127,  n in [0, 255),  w = Hann over the 255 taps,
+ *            lo/hi = the band's edges as fractions of Nyquist (taps rounded to binary32, as the product stores them);
+ *   h_b[n] = IR[(n / stride) * bands + b] * 2^-40 when stride divides n, else 0;
+ *   out[n] = sum_b sum_k g_b[k] h_b[n + 127 - k],  n in [0, bins * stride), accumulated in double. */
+ORC_API void orc_band_filter_taps(double lo, double hi, float *g) {
+    const double pi = 3.14159265358979323846;
+    for (int n = 0; n < 255; n++) {
+        int m = n - 127;
+        double ideal = m == 0 ? hi - lo : (sin(pi * hi * m) - sin(pi * lo * m)) / (pi * m);
+        double w = 0.5 - 0.5 * cos(2.0 * pi * (n + 1) / 256.0);
+        g[n] = (float)(ideal * w);
+    }
+}
+
+ORC_API void orc_synthesize_ir(const int64_t *hist, int32_t bins, int32_t bands, int32_t stride, const float *edges, float *out) {
+    int64_t n_out = (int64_t)bins * stride;
+    double *acc = (double *)calloc((size_t)(n_out > 0 ? n_out : 1), sizeof(double));
+    float g[255];
+    for (int32_t b = 0; b < bands; b++) {
+        double lo = edges ? edges[b] : (double)b / bands, hi = edges ? edges[b + 1] : (double)(b + 1) / bands;
+        orc_band_filter_taps(lo, hi, g);
+        for (int32_t bin = 0; bin < bins; bin++) {
+            int64_t q = hist[(int64_t)bin * bands + b];
+            if (q == 0) continue;
+            double h = (double)((float)q * 9.094947017729282e-13f);          /* the float view of the slot, orc_ir_to_float */
+            int64_t j = (int64_t)bin * stride;                                 /* sample the bin stands on */
+            for (int k = 0; k < 255; k++) {
+                int64_t n = j - 127 + k;                                       /* h_b[j] meets g_b[k] at out[j + k - 127] */
+                if (n >= 0 && n < n_out) acc[n] += (double)g[k] * h;
+            }
+        }
+    }
+    for (int64_t n = 0; n < n_out; n++) out[n] = (float)acc[n];
+    free(acc);
+}
+
 /* Same sum in double precision, for judging which of two float results is closer to the truth. */
 ORC_API void orc_convolve_f64(const float *in, int32_t input_length, const float *ir, int32_t ir_length,
                               int32_t accum_count, double *out, int n_threads) {

@@ -85,6 +85,8 @@ SYMBOLS = {
     "rar_trace_hits": (C.c_int, [_p, C.POINTER(TraceParams), _p, _p, _i64, C.POINTER(_i64)]),
     "rar_get_counters": (C.c_int, [_p, C.POINTER(Counters), _i32]),
     "rar_get_debug_rays": (C.c_int, [_p, _p, _i64]),
+    "rar_set_band_edges": (C.c_int, [_p, _p, _i32, _i32]),
+    "rar_synthesize_ir": (C.c_int, [_p, _i32, _p, _i64]),
     "rar_convolve": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i32]),
     "rar_convolve_begin": (C.c_int, [_p, _i32, _p, _i32, _i32, C.POINTER(_i32)]),
     "rar_poll": (C.c_int, [_p, _i32]),
@@ -93,6 +95,8 @@ SYMBOLS = {
     "rar_conv_destroy": (C.c_int, [_p]),
     "rar_conv_set_ir": (C.c_int, [_p, _i32, _p, _i32, _f32]),
     "rar_conv_set_ir_from_slot": (C.c_int, [_p, _i32, _i32, _i32]),
+    "rar_conv_set_irs": (C.c_int, [_p, _i32, _i32, _p, _i32, _i64, _f32]),
+    "rar_conv_set_irs_from_slots": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "rar_conv_update_ir": (C.c_int, [_p, _i32, _p, _i32, _f32]),
     "rar_conv_update_ir_from_slot": (C.c_int, [_p, _i32, _i32, _i32]),
     "rar_conv_reset": (C.c_int, [_p]),
@@ -315,6 +319,20 @@ class Context:
         self._ck(self._lib.rar_get_debug_rays(self._h, out.ctypes.data, n_float4))
         return out
 
+    # banded model ------------------------------------------------------------------------------
+    def set_band_edges(self, edges_hz, sample_rate: int) -> None:
+        """rar_set_band_edges; edges_hz=None restores equal-width bands."""
+        if edges_hz is None:
+            self._ck(self._lib.rar_set_band_edges(self._h, None, 0, 0))
+            return
+        e = np.ascontiguousarray(edges_hz, dtype=np.float32)
+        self._ck(self._lib.rar_set_band_edges(self._h, e.ctypes.data, len(e) - 1, sample_rate))
+
+    def synthesize_ir(self, slot: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self._lib.rar_synthesize_ir(self._h, slot, out.ctypes.data, n))
+        return out
+
     # convolution ------------------------------------------------------------------------------
     def convolve(self, slot: int, samples: np.ndarray, accum_count: int, ir_len: int) -> np.ndarray:
         x = np.ascontiguousarray(samples, dtype=np.float32)
@@ -397,6 +415,21 @@ class Convolver:
 
     def set_ir_from_slot(self, stream: int, slot: int, accum_count: int) -> None:
         self._ctx._ck(self._lib.rar_conv_set_ir_from_slot(self._h, stream, slot, accum_count))
+
+    def set_irs(self, first_stream: int, irs: np.ndarray, scale: float = 1.0) -> None:
+        """rar_conv_set_irs: irs[k] becomes the response of stream first_stream + k; no stream synchronisation."""
+        a = np.ascontiguousarray(irs, dtype=np.float32)
+        if a.ndim != 2:
+            raise ValueError("irs must be [n_streams][ir_len]")
+        self._ctx._ck(self._lib.rar_conv_set_irs(self._h, first_stream, a.shape[0], a.ctypes.data if a.size else None, a.shape[1],
+                                                 a.shape[1], scale))
+
+    def set_irs_from_slots(self, first_stream: int, slots, accum_counts) -> None:
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        ac = np.ascontiguousarray(accum_counts, dtype=np.int32)
+        if sl.shape != ac.shape:
+            raise ValueError("one accum_count per slot")
+        self._ctx._ck(self._lib.rar_conv_set_irs_from_slots(self._h, first_stream, len(sl), sl.ctypes.data, ac.ctypes.data))
 
     def update_ir(self, stream: int, ir: np.ndarray, scale: float = 1.0) -> None:
         """rar_conv_update_ir: new response, cross-faded in over the next processed block."""

@@ -92,12 +92,14 @@ __global__ void float_to_fixed_kernel(const float *__restrict__ in, long long *_
         hist[i] = quantize_energy(in[i]);
 }
 
-// H[p] = rfft([ir[pB .. pB+B), 0 x B])
-__global__ void __launch_bounds__(64 * kSub) ir_spectra_kernel(const float *__restrict__ ir, int ir_len, f2 *__restrict__ H,
-                                                                int n_part) {
+// H[p] = rfft([ir[pB .. pB+B), 0 x B]); blockIdx.y = response of a batch (ir and H advance by their strides)
+__global__ void __launch_bounds__(64 * kSub) ir_spectra_kernel(const float *__restrict__ ir, long long ir_stride, int ir_len,
+                                                                f2 *__restrict__ H, long long h_stride, int n_part) {
     __shared__ FftSmem s;
     const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
     const int p = blockIdx.x * kSub + sub;
+    ir += (long long)blockIdx.y * ir_stride;
+    H += (long long)blockIdx.y * h_stride;
     load_tables(s);
     const long long first = (long long)p * kB;
     rfft512_to_b(s, sub, i, [&](int t) -> float {
@@ -107,6 +109,121 @@ __global__ void __launch_bounds__(64 * kSub) ir_spectra_kernel(const float *__re
     if (p < n_part) {
 #pragma unroll
         for (int m = 0; m < 4; m++) H[(size_t)p * kFftM + i + 64 * m] = s.b[sub][i + 64 * m];
+    }
+}
+
+// ---- filter-bank synthesis of a broadband response from a banded slot ----------------------------
+//
+// A banded slot holds IR[bin * bands + band] (RaytraceOcclusion2D.compute:241-248); band b carries the energy that
+// arrives in the frequency range [edge_b, edge_b+1).  The broadband response a convolution needs is
+//        h[n] = sum_b (g_b * h_b)[n + D],   h_b[n] = IR[(n / stride) * bands + b] if stride divides n, else 0,
+// with g_b the 255-tap windowed-sinc band-pass filter of band b (linear phase, delay D = 127).  The ideal band-pass
+// responses of contiguous bands telescope to a unit impulse at D and the window is 1 there, so sum_b g_b is exactly
+// that impulse: a slot whose bands are all equal synthesises to that common response, sample for sample.
+// Computed per 256-sample segment as overlap-add in the frequency domain: S[p] = sum_b G_b . rfft512(h_b segment p),
+// irfft512, and the 512 results added into out[256 p - D ...].  Every output sample receives exactly two
+// contributions (segments p and p-1) onto a zeroed buffer, and a + b = b + a, so the atomic adds are deterministic.
+//
+// One launch handles a batch of slots of equal shape (blockIdx.y).  VEC (bands a multiple of 4, stride 1): a thread
+// first fetches ALL the words it will need of a chunk of 4 bands -- its four samples x 32 contiguous bytes, eight
+// independent 16-byte loads, every fetched sector fully used -- and then runs the four transforms out of registers
+// (chunks of 8 bands needed 75 registers: 3 CTAs per SM instead of 5); otherwise each band's samples are gathered
+// with strided scalar loads.
+struct BandAcc {
+    f2 v[4];
+};
+__device__ __forceinline__ void band_accumulate(BandAcc &acc, const FftSmem &s, int sub, int i, const f2 *__restrict__ gb) {
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int k = i + 64 * m;
+        const f2 x = s.b[sub][k], g = gb[k];
+        if (k == 0) {  // packed bin 0 = (DC, Nyquist), both real
+            acc.v[m].x = fmaf(x.x, g.x, acc.v[m].x);
+            acc.v[m].y = fmaf(x.y, g.y, acc.v[m].y);
+        } else {
+            acc.v[m].x += x.x * g.x - x.y * g.y;
+            acc.v[m].y += x.x * g.y + x.y * g.x;
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(64 * kSub, 4) band_synth_kernel(const __grid_constant__ BandSynthBatch batch, int bins, int bands, int stride,
+                                                                const f2 *__restrict__ G, int out_len, int n_seg, int delay) {
+    __shared__ FftSmem s;
+    const int sub = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const int p = blockIdx.x * kSub + sub;
+    const BandSynthItem it = batch.items[blockIdx.y];
+    const long long *__restrict__ hist = it.hist;
+    const float scale = it.scale;
+    load_tables(s);
+    const long long first = (long long)p * kB;
+    const long long n_samples = (long long)bins * stride;
+    BandAcc acc;
+#pragma unroll
+    for (int m = 0; m < 4; m++) acc.v[m] = f2{0.f, 0.f};
+    if (VEC) {
+        // this thread's samples of the segment: t = 2i, 2i+1 (n = i) and 2i+128, 2i+129 (n = i+64); n >= 128 is padding
+        constexpr int CH = 4;
+        for (int c0 = 0; c0 < bands; c0 += CH) {
+            float f[4][CH];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const long long g = first + 2 * i + (q & 1) + 128 * (q >> 1);
+                const bool on = p < n_seg && g < n_samples;
+                const longlong2 *src = reinterpret_cast<const longlong2 *>(hist + (on ? g : 0) * bands + c0);
+#pragma unroll
+                for (int k = 0; k < CH / 2; k++) {
+                    longlong2 w = on ? __ldcs(src + k) : make_longlong2(0, 0);
+                    f[q][2 * k] = ((float)w.x * 9.094947017729282e-13f) * scale;
+                    f[q][2 * k + 1] = ((float)w.y * 9.094947017729282e-13f) * scale;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < CH; b++) {
+                s.a[sub][i] = f2{f[0][b], f[1][b]};
+                s.a[sub][i + 64] = f2{f[2][b], f[3][b]};
+                s.a[sub][i + 128] = f2{0.f, 0.f};
+                s.a[sub][i + 192] = f2{0.f, 0.f};
+                __syncthreads();
+                fft256_inplace(s.a[sub], s.b[sub], i, s.tw, false);
+                for (int k = i; k <= kFftM / 2; k += 64) rfft_split(s.a[sub], s.b[sub], k, s.tw2);
+                __syncthreads();
+                band_accumulate(acc, s, sub, i, G + (size_t)(c0 + b) * kFftM);
+                __syncthreads();  // s.a / s.b are reused by the next band
+            }
+        }
+    } else {
+        for (int b = 0; b < bands; b++) {
+            rfft512_to_b(s, sub, i, [&](int t) -> float {
+                const long long g = first + t;
+                if (p >= n_seg || t >= kB || g >= n_samples) return 0.0f;
+                long long bin = g;
+                if (stride > 1) {
+                    bin = g / stride;
+                    if (bin * stride != g) return 0.0f;
+                }
+                return ((float)__ldg(hist + bin * bands + b) * 9.094947017729282e-13f) * scale;
+            });
+            band_accumulate(acc, s, sub, i, G + (size_t)b * kFftM);
+            __syncthreads();  // s.a / s.b are reused by the next band
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) s.b[sub][i + 64 * m] = acc.v[m];
+    __syncthreads();
+    irfft512_from_b(s, sub, i);
+    if (p < n_seg) {
+        const float inv = 1.0f / (float)kFftM;
+        float *__restrict__ out = it.out;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int n = i + 64 * m;
+            const f2 v = s.a[sub][n];
+            const long long o = first + 2 * n - delay;
+            if (o >= 0 && o < out_len) atomicAdd(out + o, v.x * inv);
+            if (o + 1 >= 0 && o + 1 < out_len) atomicAdd(out + o + 1, v.y * inv);
+        }
     }
 }
 
@@ -408,9 +525,31 @@ cudaError_t launch_float_to_fixed(const float *in, long long *hist, long long n,
 }
 
 cudaError_t launch_ir_spectra(const float *ir_f, int ir_len, float2 *H, int n_part, int block, cudaStream_t s) {
+    return launch_ir_spectra_batch(ir_f, 0, ir_len, H, 0, n_part, 1, block, s);
+}
+
+cudaError_t launch_ir_spectra_batch(const float *ir_f, long long ir_stride, int ir_len, float2 *H, long long h_stride, int n_part,
+                                    int n_items, int block, cudaStream_t s) {
     if (block != kB) return cudaErrorInvalidValue;
-    if (n_part <= 0) return cudaSuccess;
-    ir_spectra_kernel<<<blocks_for(n_part, kSub), 64 * kSub, 0, s>>>(ir_f, ir_len, reinterpret_cast<f2 *>(H), n_part);
+    if (n_part <= 0 || n_items <= 0) return cudaSuccess;
+    ir_spectra_kernel<<<dim3(blocks_for(n_part, kSub), n_items), 64 * kSub, 0, s>>>(ir_f, ir_stride, ir_len, reinterpret_cast<f2 *>(H),
+                                                                                     h_stride, n_part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_band_synth(const BandSynthBatch &batch, int n_items, int bins, int bands, int stride, const float2 *G, int out_len,
+                              cudaStream_t s) {
+    if (n_items <= 0 || bins <= 0 || bands <= 0 || stride <= 0 || out_len <= 0) return cudaSuccess;
+    if (n_items > kBandSynthBatch) return cudaErrorInvalidValue;
+    const long long n_samples = (long long)bins * stride;
+    const int n_seg = (int)((n_samples + kB - 1) / kB);
+    const dim3 grid(blocks_for(n_seg, kSub), n_items);
+    if (bands % 4 == 0 && stride == 1)
+        band_synth_kernel<true><<<grid, 64 * kSub, 0, s>>>(batch, bins, bands, stride, reinterpret_cast<const f2 *>(G), out_len, n_seg,
+                                                           kBandFilterDelay);
+    else
+        band_synth_kernel<false><<<grid, 64 * kSub, 0, s>>>(batch, bins, bands, stride, reinterpret_cast<const f2 *>(G), out_len, n_seg,
+                                                            kBandFilterDelay);
     return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@
 // There is no CPU path here: every compute entry point needs a CUDA device and fails otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -27,7 +28,9 @@ struct Slot {
     long long cap_words = 0;
     int impulse_length = 0;
     int bands = 0;
+    int time_stride = 1;  // samples per time bin (the time_divisor of the traces that filled the slot); 0: not an integer
     bool configured = false;
+    bool aliased = false;  // rar_ir_device_ptr handed the histogram out: cached spectra are never trusted again
     // cached spectra of the slot's IR partitions (one-shot convolution)
     float2 *d_H = nullptr;
     int H_cap = 0;  // partitions allocated
@@ -136,6 +139,13 @@ struct rar_context {
     bool walls_are_bounded = false; // every coordinate finite and within 2^30 (rar_layout.h walls_bounded)
 
     std::vector<Slot> slots;
+    // filter bank of the banded model: edges as fractions of Nyquist (empty: equal-width bands), spectra per band count
+    std::vector<float> band_edges;
+    DevBuf<float2> d_band_G;
+    int band_G_bands = 0;  // band count d_band_G was built for (0: stale)
+    DevBuf<float> d_synth;  // synthesised broadband response (scratch)
+    PinnedBuf<float> h_band_taps;
+    DevBuf<float> d_band_taps;
     DevBuf<unsigned long long> d_counters;  // 5 counters + 1 hit count
     DevBuf<f4> d_debug;
     int debug_entries = 0;
@@ -155,6 +165,10 @@ struct rar_convolver {
     DevBuf<float2> H, fdl, partial;
     DevBuf<float> prev, d_in, d_out, d_irf;
     PinnedBuf<float> h_ir;
+    // batched response loads (rar_conv_set_irs*): device scratch for a group of responses, two pinned staging halves
+    DevBuf<float> d_batch;
+    PinnedBuf<float> h_batch;
+    cudaEvent_t batch_done[2] = {nullptr, nullptr};  // the staging half may be rewritten once its copy has completed
     // cross-faded impulse-response updates (allocated on first use)
     DevBuf<float2> H2, partial2;   // new spectra of the fading streams, their partial sums
     DevBuf<int> d_fade, d_list;    // [S] flags, compact list of fading streams
@@ -300,10 +314,65 @@ int acquire_ticket(rar_context *ctx) {
     return (int)ctx->tickets.size() - 1;
 }
 
+// Spectra of the band filters for `bands` bands (built on first use and after rar_set_band_edges).
+int ensure_band_filters(rar_context *ctx, int bands) {
+    if (ctx->band_G_bands == bands) return RAR_OK;
+    if (!ctx->band_edges.empty() && (int)ctx->band_edges.size() != bands + 1)
+        return fail(ctx, RAR_ERR_STATE, "rar_set_band_edges was called for a different band count than this slot has");
+    const size_t taps = (size_t)bands * kBlock;  // each filter zero-padded to one partition
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffers may still feed an earlier upload
+    RAR_CUDA(ctx, ctx->h_band_taps.reserve(taps));
+    RAR_CUDA(ctx, ctx->d_band_taps.reserve(taps));
+    RAR_CUDA(ctx, ctx->d_band_G.reserve(taps));
+    std::memset(ctx->h_band_taps.p, 0, taps * sizeof(float));
+    for (int b = 0; b < bands; b++) {
+        const double lo = ctx->band_edges.empty() ? (double)b / bands : ctx->band_edges[b];
+        const double hi = ctx->band_edges.empty() ? (double)(b + 1) / bands : ctx->band_edges[b + 1];
+        band_filter_taps(lo, hi, ctx->h_band_taps.p + (size_t)b * kBlock);
+    }
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_band_taps.p, ctx->h_band_taps.p, taps * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // one partition per band: H[b] = rfft512([g_b, 0 ...])
+    RAR_CUDA(ctx, launch_ir_spectra(ctx->d_band_taps.p, (int)taps, ctx->d_band_G.p, bands, kBlock, ctx->stream));
+    ctx->launches++;
+    ctx->band_G_bands = bands;
+    return RAR_OK;
+}
+
+// Samples of the broadband response a slot stands for: bins x samples per bin.
+long long slot_ir_samples(const Slot &S) { return (long long)S.impulse_length * (S.time_stride > 0 ? S.time_stride : 1); }
+
+int check_convolvable(rar_context *ctx, const Slot &S) {
+    if (S.bands > 1 && S.time_stride <= 0)
+        return fail(ctx, RAR_ERR_UNSUPPORTED, "the slot was traced with a non-integer time_divisor: no sample grid to synthesise on");
+    if (slot_ir_samples(S) > 0x7fffffffLL - 2 * kBlock) return fail(ctx, RAR_ERR_UNSUPPORTED, "impulse response too long");
+    return RAR_OK;
+}
+
+// The slot's response as floats on the device, scaled: the histogram itself for a broadband slot, the filter-bank
+// synthesis for a banded one (out must hold slot_ir_samples(S) floats).
+int slot_response(rar_context *ctx, Slot &S, float scale, float *d_out) {
+    const int n = (int)slot_ir_samples(S);
+    if (S.bands == 1 && S.time_stride == 1) {
+        RAR_CUDA(ctx, launch_fixed_to_float(S.d_hist, d_out, n, scale, ctx->stream));
+        ctx->launches++;
+        return RAR_OK;
+    }
+    int rc = ensure_band_filters(ctx, S.bands);
+    if (rc != RAR_OK) return rc;
+    BandSynthBatch batch;
+    std::memset(&batch, 0, sizeof batch);
+    batch.items[0] = BandSynthItem{S.d_hist, d_out, scale, 0};
+    RAR_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(float), ctx->stream));
+    RAR_CUDA(ctx, launch_band_synth(batch, 1, S.impulse_length, S.bands, S.time_stride, ctx->d_band_G.p, n, ctx->stream));
+    ctx->launches++;
+    return RAR_OK;
+}
+
 // Makes the cached partition spectra of a slot current.
 int ensure_slot_spectra(rar_context *ctx, Slot &S) {
-    const int n_part = (S.impulse_length + kBlock - 1) / kBlock;
-    if (S.H_valid && S.H_parts == n_part) return RAR_OK;
+    const int n_samples = (int)slot_ir_samples(S);
+    const int n_part = (n_samples + kBlock - 1) / kBlock;
+    if (S.H_valid && !S.aliased && S.H_parts == n_part) return RAR_OK;
     if (n_part > S.H_cap) {
         if (S.d_H) cudaFree(S.d_H);
         S.d_H = nullptr;
@@ -311,10 +380,11 @@ int ensure_slot_spectra(rar_context *ctx, Slot &S) {
         RAR_CUDA(ctx, cudaMalloc((void **)&S.d_H, (size_t)(n_part + 8) * kBlock * sizeof(float2)));
         S.H_cap = n_part + 8;
     }
-    RAR_CUDA(ctx, ctx->d_irf.reserve((size_t)S.impulse_length + 1));
-    RAR_CUDA(ctx, launch_fixed_to_float(S.d_hist, ctx->d_irf.p, S.impulse_length, 1.0f, ctx->stream));
-    RAR_CUDA(ctx, launch_ir_spectra(ctx->d_irf.p, S.impulse_length, S.d_H, n_part, kBlock, ctx->stream));
-    ctx->launches += 2;
+    RAR_CUDA(ctx, ctx->d_irf.reserve((size_t)n_samples + 1));
+    int rc = slot_response(ctx, S, 1.0f, ctx->d_irf.p);
+    if (rc != RAR_OK) return rc;
+    RAR_CUDA(ctx, launch_ir_spectra(ctx->d_irf.p, n_samples, S.d_H, n_part, kBlock, ctx->stream));
+    ctx->launches += 1;
     S.H_parts = n_part;
     S.H_valid = true;
     return RAR_OK;
@@ -399,6 +469,10 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_clip_out.release();
     ctx->d_listeners.release();
     ctx->d_listener_hists.release();
+    ctx->d_band_G.release();
+    ctx->d_synth.release();
+    ctx->h_band_taps.release();
+    ctx->d_band_taps.release();
     ctx->d_grid_start.release();
     ctx->d_grid_items.release();
     ctx->d_grid_geo.release();
@@ -474,6 +548,66 @@ int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int3
     return RAR_OK;
 }
 
+// ---- filter bank of the banded model ------------------------------------------------------------------
+
+}  // extern "C"
+
+// g[n] = w[n] (hi sinc(hi m) - lo sinc(lo m)), m = n - 127, w = Hann over the 255 taps (nonzero at both ends).
+// Contiguous bands telescope: sum_b g_b[n] = w[n] sinc(m) = [n == 127].
+void rar::band_filter_taps(double lo, double hi, float *g) {
+    const double pi = 3.14159265358979323846;
+    for (int n = 0; n < kBandFilterTaps; n++) {
+        const int m = n - kBandFilterDelay;
+        const double ideal = m == 0 ? hi - lo : (std::sin(pi * hi * m) - std::sin(pi * lo * m)) / (pi * m);
+        const double w = 0.5 - 0.5 * std::cos(2.0 * pi * (n + 1) / (kBandFilterTaps + 1));
+        g[n] = (float)(ideal * w);
+    }
+}
+
+extern "C" {
+
+int rar_set_band_edges(rar_context *ctx, const float *edges_hz, int32_t bands, int32_t sample_rate) {
+    RAR_ENTER(ctx);
+    if (!edges_hz) {  // back to the default: equal-width bands
+        ctx->band_edges.clear();
+        ctx->band_G_bands = 0;
+        return RAR_OK;
+    }
+    if (bands < 1 || bands > 128 || sample_rate <= 0) return fail(ctx, RAR_ERR_INVALID, "bands must be 1..128 and sample_rate positive");
+    const double nyq = 0.5 * sample_rate;
+    std::vector<float> e(bands + 1);
+    for (int b = 0; b <= bands; b++) {
+        e[b] = (float)(edges_hz[b] / nyq);
+        if (!(e[b] >= 0.0f && e[b] <= 1.0f) || (b > 0 && !(e[b] > e[b - 1])))
+            return fail(ctx, RAR_ERR_INVALID, "band edges must ascend strictly within [0, sample_rate / 2]");
+    }
+    if (e[0] != 0.0f || e[bands] != 1.0f)
+        return fail(ctx, RAR_ERR_INVALID, "band edges must start at 0 and end at sample_rate / 2 (the bands tile the spectrum)");
+    ctx->band_edges.swap(e);
+    ctx->band_G_bands = 0;
+    return RAR_OK;
+}
+
+int rar_synthesize_ir(rar_context *ctx, int32_t slot, float *out, int64_t n) {
+    RAR_ENTER(ctx);
+    Slot *S = get_slot(ctx, slot, false);
+    if (!out || n < 0) return fail(ctx, RAR_ERR_INVALID, "bad output array");
+    if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
+    int rc = check_convolvable(ctx, *S);
+    if (rc != RAR_OK) return rc;
+    const long long have = std::min<long long>(n, slot_ir_samples(*S));
+    if (slot_ir_samples(*S) > 0) {
+        RAR_CUDA(ctx, ctx->d_synth.reserve((size_t)slot_ir_samples(*S) + 1));
+        rc = slot_response(ctx, *S, 1.0f, ctx->d_synth.p);
+        if (rc != RAR_OK) return rc;
+        if (have > 0)
+            RAR_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_synth.p, (size_t)have * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > have) std::memset(out + have, 0, (size_t)(n - have) * sizeof(float));
+    return RAR_OK;
+}
+
 // ---- IR slots ---------------------------------------------------------------------------------------
 
 int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length, int32_t bands) {
@@ -483,6 +617,9 @@ int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length, int32_t
     if (impulse_length < 0 || bands < 1) return fail(ctx, RAR_ERR_INVALID, "bad impulse_length/bands");
     const long long words = (long long)impulse_length * bands;
     if (words > S->cap_words) {
+        if (S->d_hist && S->aliased)
+            return fail(ctx, RAR_ERR_STATE, "the slot must grow, but rar_ir_device_ptr handed out its device address, which would "
+                                            "dangle: configure the slot at its largest size first, or use another slot");
         if (S->d_hist) {
             RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(S->d_hist);
@@ -495,6 +632,7 @@ int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length, int32_t
     if (words > 0) RAR_CUDA(ctx, cudaMemsetAsync(S->d_hist, 0, (size_t)words * sizeof(long long), ctx->stream));
     S->impulse_length = impulse_length;
     S->bands = bands;
+    S->time_stride = 1;
     S->configured = true;
     S->H_valid = false;
     return RAR_OK;
@@ -586,7 +724,8 @@ int rar_ir_device_ptr(rar_context *ctx, int32_t slot, void **device_ptr, int64_t
     if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
     if (device_ptr) *device_ptr = S->d_hist;
     if (n_words) *n_words = (int64_t)S->impulse_length * S->bands;
-    S->H_valid = false;  // the caller may modify the histogram (all-reduce)
+    S->H_valid = false;  // the caller may modify the histogram (all-reduce) at any later time:
+    S->aliased = true;   // cached spectra of this slot are never trusted again
     return RAR_OK;
 }
 
@@ -913,6 +1052,11 @@ static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, i
         ctx->launches += launched;
     }
     S->H_valid = false;
+    {   // the sample grid the slot's bins stand on (RaytraceOcclusion2D.compute:241-243: bin = (int)(t*SampleRate/WindowSize))
+        const float d = params->time_divisor;
+        const int stride = (d >= 1.0f && d <= 65536.0f && d == std::floor(d)) ? (int)d : 0;
+        S->time_stride = stride;
+    }
     return RAR_OK;
 }
 
@@ -1043,8 +1187,11 @@ int rar_convolve_begin(rar_context *ctx, int32_t slot, const float *in, int32_t 
     if (in_len < 0 || (in_len > 0 && !in)) return fail(ctx, RAR_ERR_INVALID, "bad input array");
     Slot *S = get_slot(ctx, slot, false);
     if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured (call rar_ir_clear first)");
-    if (S->bands != 1) return fail(ctx, RAR_ERR_UNSUPPORTED, "convolution needs a broadband (bands == 1) slot");
-    const int ir_len = S->impulse_length;
+    {
+        int rc = check_convolvable(ctx, *S);
+        if (rc != RAR_OK) return rc;
+    }
+    const int ir_len = (int)slot_ir_samples(*S);  // a banded slot is convolved through its filter-bank synthesis
     const int out_len = in_len + ir_len;  // AudioConvolve.compute:15
 
     const int id = acquire_ticket(ctx);
@@ -1184,6 +1331,9 @@ int rar_conv_destroy(rar_convolver *cv) {
     cv->H.release(); cv->fdl.release(); cv->partial.release(); cv->prev.release();
     cv->d_in.release(); cv->d_out.release(); cv->d_irf.release(); cv->h_ir.release();
     cv->H2.release(); cv->partial2.release(); cv->d_fade.release(); cv->d_list.release();
+    cv->d_batch.release(); cv->h_batch.release();
+    for (cudaEvent_t &e : cv->batch_done)
+        if (e) cudaEventDestroy(e);
     delete cv;
     return RAR_OK;
 }
@@ -1232,15 +1382,122 @@ static int conv_set_ir_from_slot_impl(rar_convolver *cv, int32_t stream, int32_t
     if (stream < 0 || stream >= cv->c.n_streams) return fail(ctx, RAR_ERR_INVALID, "stream index out of range");
     Slot *S = get_slot(ctx, slot, false);
     if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured");
-    if (S->bands != 1) return fail(ctx, RAR_ERR_UNSUPPORTED, "convolution needs a broadband (bands == 1) slot");
-    if (S->impulse_length > cv->max_ir_len) return fail(ctx, RAR_ERR_INVALID, "slot IR is longer than max_ir_len");
+    int rc = check_convolvable(ctx, *S);
+    if (rc != RAR_OK) return rc;
+    const long long ir_len = slot_ir_samples(*S);
+    if (ir_len > cv->max_ir_len) return fail(ctx, RAR_ERR_INVALID, "slot IR is longer than max_ir_len");
     const float scale = accum_count > 0 ? 1.0f / (float)accum_count : 0.0f;
     float2 *H = nullptr;
-    int rc = conv_target(cv, stream, fade, &H);
+    rc = conv_target(cv, stream, fade, &H);
     if (rc != RAR_OK) return rc;
-    RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, cv->d_irf.p, S->impulse_length, scale, ctx->stream));
-    RAR_CUDA(ctx, launch_ir_spectra(cv->d_irf.p, S->impulse_length, H, cv->c.n_part, cv->c.block, ctx->stream));
-    ctx->launches += 2;
+    rc = slot_response(ctx, *S, scale, cv->d_irf.p);
+    if (rc != RAR_OK) return rc;
+    RAR_CUDA(ctx, launch_ir_spectra(cv->d_irf.p, (int)ir_len, H, cv->c.n_part, cv->c.block, ctx->stream));
+    ctx->launches += 1;
+    return RAR_OK;
+}
+
+
+// Responses of n consecutive streams in one call (config 5 loads 256 of them): staged through two pinned halves that
+// alternate, so the host fills one while the other is on its way, with no stream synchronisation -- only an event
+// wait when a half is needed again -- and one spectra launch per group instead of one per stream.
+int rar_conv_set_irs(rar_convolver *cv, int32_t first_stream, int32_t n, const float *irs, int32_t ir_len, int64_t ir_stride,
+                     float scale) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    StreamConv &c = cv->c;
+    if (n < 0 || first_stream < 0 || (long long)first_stream + n > c.n_streams) return fail(ctx, RAR_ERR_INVALID, "stream range out of bounds");
+    if (ir_len < 0 || ir_len > cv->max_ir_len || ir_stride < ir_len || (n > 0 && ir_len > 0 && !irs)) return fail(ctx, RAR_ERR_INVALID, "bad ir array");
+    if (n == 0) return RAR_OK;
+    if (cv->fade.empty()) cv->fade.assign(c.n_streams, 0);
+    const size_t row = (size_t)c.n_part * c.block;                       // floats per staged response (zero padded)
+    size_t group = (size_t)(16u << 20) / (row * sizeof(float));          // ~16 MB per staging half
+    if (group < 1) group = 1;
+    if (group > (size_t)n) group = (size_t)n;
+    RAR_CUDA(ctx, cv->h_batch.reserve(2 * group * row));
+    RAR_CUDA(ctx, cv->d_batch.reserve(2 * group * row));
+    for (cudaEvent_t &e : cv->batch_done)
+        if (!e) RAR_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int half = 0;
+    for (int s0 = 0; s0 < n; s0 += (int)group, half ^= 1) {
+        const int g = (int)std::min<size_t>(group, (size_t)(n - s0));
+        float *h = cv->h_batch.p + (size_t)half * group * row, *d = cv->d_batch.p + (size_t)half * group * row;
+        RAR_CUDA(ctx, cudaEventSynchronize(cv->batch_done[half]));       // completes at once for a never-recorded event
+        for (int k = 0; k < g; k++) {
+            const float *src = irs + (size_t)(s0 + k) * ir_stride;
+            float *dst = h + (size_t)k * row;
+            for (int i = 0; i < ir_len; i++) dst[i] = src[i] * scale;
+            std::memset(dst + ir_len, 0, (row - ir_len) * sizeof(float));
+            cv->fade[first_stream + s0 + k] = 0;                         // a hard set cancels a pending cross-fade
+        }
+        RAR_CUDA(ctx, cudaMemcpyAsync(d, h, (size_t)g * row * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        RAR_CUDA(ctx, launch_ir_spectra_batch(d, (long long)row, (int)row, c.H + (size_t)(first_stream + s0) * row, (long long)row, c.n_part,
+                                              g, c.block, ctx->stream));
+        RAR_CUDA(ctx, cudaEventRecord(cv->batch_done[half], ctx->stream));
+        ctx->launches++;
+    }
+    return RAR_OK;
+}
+
+// The same from traced slots, all on the device: stream first_stream + k takes slot slots[k] scaled by
+// 1 / accum_counts[k] (banded slots through their filter-bank synthesis, in groups of one launch).
+int rar_conv_set_irs_from_slots(rar_convolver *cv, int32_t first_stream, int32_t n, const int32_t *slots, const int32_t *accum_counts) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    StreamConv &c = cv->c;
+    if (n < 0 || first_stream < 0 || (long long)first_stream + n > c.n_streams) return fail(ctx, RAR_ERR_INVALID, "stream range out of bounds");
+    if (n > 0 && (!slots || !accum_counts)) return fail(ctx, RAR_ERR_INVALID, "null slot / accum_count array");
+    if (n == 0) return RAR_OK;
+    if (cv->fade.empty()) cv->fade.assign(c.n_streams, 0);
+    const Slot *S0 = get_slot(ctx, slots[0], false);
+    if (!S0 || !S0->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured");
+    for (int k = 0; k < n; k++) {
+        Slot *S = get_slot(ctx, slots[k], false);
+        if (!S || !S->configured) return fail(ctx, RAR_ERR_STATE, "slot is not configured");
+        if (S->impulse_length != S0->impulse_length || S->bands != S0->bands || S->time_stride != S0->time_stride)
+            return fail(ctx, RAR_ERR_INVALID, "the slots of one call must have the same shape");
+    }
+    int rc = check_convolvable(ctx, *S0);
+    if (rc != RAR_OK) return rc;
+    const long long ir_len = slot_ir_samples(*S0);
+    if (ir_len > cv->max_ir_len) return fail(ctx, RAR_ERR_INVALID, "slot IR is longer than max_ir_len");
+    const bool banded = !(S0->bands == 1 && S0->time_stride == 1);
+    if (banded) {
+        rc = ensure_band_filters(ctx, S0->bands);
+        if (rc != RAR_OK) return rc;
+    }
+    const size_t row = (size_t)c.n_part * c.block;
+    const int group = std::min(n, kBandSynthBatch);
+    RAR_CUDA(ctx, cv->d_batch.reserve((size_t)group * row));             // stream order serialises the groups' use of it
+    for (int s0 = 0; s0 < n; s0 += group) {
+        const int g = std::min(group, n - s0);
+        float *d = cv->d_batch.p;
+        if (banded) {
+            BandSynthBatch batch;
+            std::memset(&batch, 0, sizeof batch);
+            for (int k = 0; k < g; k++) {
+                const int acc = accum_counts[s0 + k];
+                batch.items[k] = BandSynthItem{get_slot(ctx, slots[s0 + k], false)->d_hist, d + (size_t)k * row,
+                                               acc > 0 ? 1.0f / (float)acc : 0.0f, 0};
+            }
+            RAR_CUDA(ctx, cudaMemsetAsync(d, 0, (size_t)g * row * sizeof(float), ctx->stream));
+            RAR_CUDA(ctx, launch_band_synth(batch, g, S0->impulse_length, S0->bands, S0->time_stride, ctx->d_band_G.p, (int)ir_len, ctx->stream));
+            ctx->launches++;
+        } else {
+            for (int k = 0; k < g; k++) {
+                const int acc = accum_counts[s0 + k];
+                RAR_CUDA(ctx, launch_fixed_to_float(get_slot(ctx, slots[s0 + k], false)->d_hist, d + (size_t)k * row, ir_len,
+                                                    acc > 0 ? 1.0f / (float)acc : 0.0f, ctx->stream));
+                ctx->launches++;
+            }
+        }
+        RAR_CUDA(ctx, launch_ir_spectra_batch(d, (long long)row, (int)ir_len, c.H + (size_t)(first_stream + s0) * row, (long long)row,
+                                              c.n_part, g, c.block, ctx->stream));
+        ctx->launches++;
+        for (int k = 0; k < g; k++) cv->fade[first_stream + s0 + k] = 0;
+    }
     return RAR_OK;
 }
 

@@ -93,6 +93,30 @@ cudaError_t launch_float_to_fixed(const float *in, long long *hist, long long n,
 // Spectra of the IR partitions: H[p] = rfft([ir[p*B .. p*B+B), 0...0]) for p in [0, n_part).
 // ir_f (float, already scaled) has ir_len valid samples.
 cudaError_t launch_ir_spectra(const float *ir_f, int ir_len, float2 *H, int n_part, int block, cudaStream_t s);
+// The same for n_items responses: response k at ir_f + k*ir_stride (floats), its spectra at H + k*h_stride (float2).
+cudaError_t launch_ir_spectra_batch(const float *ir_f, long long ir_stride, int ir_len, float2 *H, long long h_stride, int n_part,
+                                    int n_items, int block, cudaStream_t s);
+
+// Filter bank of the banded model: 255-tap windowed-sinc band-pass filters, linear phase.
+constexpr int kBandFilterTaps = 255;
+constexpr int kBandFilterDelay = 127;
+// Taps of band [lo, hi) (edges as fractions of the Nyquist frequency), g[kBandFilterTaps].
+void band_filter_taps(double lo, double hi, float *g);
+// out[n] += sum_b (g_b * h_b)[n + delay], h_b[n] = hist[(n/stride)*bands + b] * 2^-40 * scale when stride divides n; G =
+// packed half spectra of the band filters [bands][256].  A batch of n_items slots of equal shape, descriptors in
+// the launch arguments; every item's out (out_len floats) must have been zeroed.
+struct BandSynthItem {
+    const long long *hist;
+    float *out;
+    float scale;
+    int pad;
+};
+constexpr int kBandSynthBatch = 32;
+struct BandSynthBatch {
+    BandSynthItem items[kBandSynthBatch];
+};
+cudaError_t launch_band_synth(const BandSynthBatch &batch, int n_items, int bins, int bands, int stride, const float2 *G, int out_len,
+                              cudaStream_t s);
 
 // One-shot convolution (AudioConvolve semantics):
 //  X[j] = rfft([x[(j-1)B .. jB), x[jB .. (j+1)B)]) with |x| <= 1e-4 zeroed, j in [0, n_xwin)

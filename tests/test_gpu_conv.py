@@ -245,3 +245,29 @@ def test_streaming_ir_update_from_traced_slot(ctx, oracle):
         want = a if k < 20 else (a + w * (b - a) if k == 20 else b)
         assert rel_l2(y, want) <= TOL, k
     cv.destroy()
+
+
+def test_batched_response_load_equals_per_stream_loads(ctx, oracle):
+    """rar_conv_set_irs (one call, alternating pinned staging halves, no stream synchronisation) against rar_conv_set_ir
+    per stream; the responses are long enough for several staging groups."""
+    rng = np.random.default_rng(12)
+    S, n = 24, 400_000                                   # 24 x 1.6 MB: three 16 MB staging groups
+    irs = (rng.standard_normal((S, n)) * np.exp(-np.arange(n) / 50_000.0)).astype(np.float32) * np.float32(0.02)
+    x = rng.uniform(-1, 1, (S, 256 * 3)).astype(np.float32)
+    out = []
+    for batched in (True, False):
+        cv = _capi.Convolver(ctx, S, 256, n)
+        try:
+            if batched:
+                cv.set_irs(0, irs, 0.5)
+                irs_after = irs.copy()                    # the call has copied: the caller's array is free again
+            else:
+                for s in range(S):
+                    cv.set_ir(s, irs[s], 0.5)
+            out.append(np.concatenate([cv.process(x[:, k * 256:(k + 1) * 256]) for k in range(3)], axis=1))
+        finally:
+            cv.destroy()
+    assert np.array_equal(out[0], out[1]) and out[0].any()
+    assert np.array_equal(irs, irs_after)
+    want = oracle.convolve(x[5], irs[5] * np.float32(0.5), 1)[: 256 * 3]
+    assert rel_l2(out[0][5], want) <= 1e-4

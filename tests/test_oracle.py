@@ -210,3 +210,38 @@ def test_openmp_result_is_thread_count_independent(oracle):
     a = oracle.trace(oracle_walls(oracle, sc.walls), P, n_threads=1).hist
     b = oracle.trace(oracle_walls(oracle, sc.walls), P, n_threads=5).hist
     assert np.array_equal(a, b)
+
+
+def test_band_filter_bank_properties(oracle):
+    """The banded model's filter bank (this build's definition, include/rar2d.h): the band filters sum to a unit
+    impulse at the filter delay; each is linear-phase; synthesis is linear, shift-invariant on the sample grid, and
+    equals scipy's convolution of the taps with the band responses."""
+    from scipy.signal import fftconvolve
+    for bands in (2, 8, 128):
+        g = np.stack([oracle.band_filter_taps(b / bands, (b + 1) / bands) for b in range(bands)]).astype(np.float64)
+        delta = np.zeros(255)
+        delta[127] = 1.0
+        assert np.abs(g.sum(0) - delta).max() < 1e-6
+        assert np.abs(g - g[:, ::-1]).max() < 1e-7                      # symmetric about tap 127
+    rng = np.random.default_rng(1)
+    bins, bands = 900, 8
+    ir = (rng.random((bins, bands)) * (rng.random((bins, bands)) < 0.1) * 1e-3).astype(np.float32)
+    hist = np.array([oracle.lib().orc_quantize(float(v)) for v in ir.ravel()], np.int64)
+    out = oracle.synthesize_ir(hist, bins, bands)
+    hf = oracle.ir_to_float(hist).reshape(bins, bands).astype(np.float64)
+    want = np.zeros(bins + 254)
+    for b in range(bands):
+        want += fftconvolve(hf[:, b], oracle.band_filter_taps(b / bands, (b + 1) / bands).astype(np.float64))
+    assert np.abs(out - want[127:127 + bins]).max() <= 1e-9
+    # a band that carries everything alone is band-limited: energy outside [lo, hi] is small
+    one = np.zeros((bins, bands), np.int64)
+    one[100, 3] = 1 << 38
+    spec = np.abs(np.fft.rfft(oracle.synthesize_ir(one.ravel(), bins, bands), 4096))
+    f = np.arange(len(spec)) / (len(spec) - 1)
+    inside = (f > 3 / 8 - 0.02) & (f < 4 / 8 + 0.02)
+    assert (spec[~inside] ** 2).sum() < 2e-3 * (spec ** 2).sum()
+    # coarse time bins: bin k stands on sample k * stride
+    s4 = oracle.synthesize_ir(hist, bins, bands, 4)
+    up = np.zeros((bins * 4, bands), np.int64)
+    up[::4] = hist.reshape(bins, bands)
+    assert np.array_equal(s4, oracle.synthesize_ir(up.ravel(), bins * 4, bands, 1))
