@@ -106,6 +106,18 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_conv_process_device(IntPtr conv, IntPtr dIn, IntPtr dOut);
         [DllImport(Lib)] public static extern long rar_conv_bytes_per_block(IntPtr conv);
 
+        // AudioManager's ring as a native lock-free SPSC structure (PushSamples on the main thread, OnAudioFilterRead on the audio thread)
+        [DllImport(Lib)] public static extern int rar_ring_create(int outputSampleRate, float reverbDuration, out IntPtr ring);
+        [DllImport(Lib)] public static extern int rar_ring_destroy(IntPtr ring);
+        [DllImport(Lib)] public static extern int rar_ring_reset(IntPtr ring);
+        [DllImport(Lib)] public static extern int rar_ring_stop(IntPtr ring);
+        [DllImport(Lib)] public static extern int rar_ring_size(IntPtr ring);
+        [DllImport(Lib)] public static extern int rar_ring_is_pinned(IntPtr ring);
+        [DllImport(Lib)] public static extern long rar_ring_frames_drained(IntPtr ring);
+        [DllImport(Lib)] public static extern int rar_ring_push(IntPtr ring, [In] float[] samples, int n, long sampleOffset);
+        [DllImport(Lib)] public static extern int rar_ring_drain(IntPtr ring, [In, Out] float[] data, int dataLength, int channels);
+        [DllImport(Lib)] public static extern int rar_conv_process_to_ring(IntPtr conv, [In] float[] input, [In] IntPtr[] rings, long sampleOffset);
+
         [DllImport(Lib)] public static extern int rar_device_info(IntPtr ctx, out int smCount, out int smClockKhz, out int smemOptinBytes);
         [DllImport(Lib)] public static extern int rar_measure_fp32_peak(IntPtr ctx, out double laneOpsPerSecond);
         [DllImport(Lib)] public static extern int rar_selftest_arithmetic(IntPtr ctx, long nSamples, uint seed, [Out] ulong[] mismatches5);

@@ -122,6 +122,7 @@ typedef struct rar_counters {
 
 typedef struct rar_context rar_context;
 typedef struct rar_convolver rar_convolver;
+typedef struct rar_ring rar_ring;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 
@@ -366,6 +367,35 @@ RAR_API int rar_conv_process(rar_convolver *conv, const float *in, float *out);
 RAR_API int rar_conv_process_device(rar_convolver *conv, const float *d_in, float *d_out);
 /* Algorithmic HBM bytes one process call moves (delay-line + IR spectra reads, spectrum write, I/O). */
 RAR_API int64_t rar_conv_bytes_per_block(const rar_convolver *conv);
+
+/* ---- playback ring ------------------------------------------------------------------
+ * AudioManager.cs as a native structure the C# AudioManager can bind: a float ring in pinned host memory, lock-free
+ * for ONE producer thread (Unity main thread: PushSamples) and ONE consumer thread (audio thread: OnAudioFilterRead).
+ * The reference guards both with lock(bufferLock) (AudioManager.cs:48,59); here the consumer is wait-free
+ * (exchange-with-zero per sample) and the producer adds with a compare-exchange per sample, so the audio callback can
+ * never wait for a 76 800-sample push.  Needs no GPU (falls back to ordinary memory when CUDA is unavailable).
+ *
+ *   rar_ring_create   AudioManager.StartStreaming (:26-36): bufferSize = CeilToInt(sampleRate * (reverbDuration + 1)),
+ *                     silent, read head 0, streaming.
+ *   rar_ring_reset    StartStreaming again on the same ring (not while the consumer is inside rar_ring_drain).
+ *   rar_ring_stop     StopStreaming (:38-43): push and drain become no-ops, like `if (!isStreaming) return`.
+ *   rar_ring_push     PushSamples (:45-54): ring[(sample_offset % size + i) % size] += samples[i]; sample_offset >= 0.
+ *   rar_ring_drain    OnAudioFilterRead (:56-69): for each of data_length / channels frames, the sample at the read
+ *                     head goes to every channel of the frame and is zeroed; the rest of `data` is left untouched.
+ *   rar_ring_frames_drained  frames handed out since creation / reset (monotone): lets a producer pace itself.
+ *   rar_conv_process_to_ring one block of the streaming convolver (like rar_conv_process, `in` = host [n_streams][block])
+ *                     whose output goes straight into rings: stream s is pushed to rings[s] at sample_offset
+ *                     (rings[s] == NULL: that stream's output is dropped).  Blocking; producer-side call. */
+RAR_API int rar_ring_create(int32_t output_sample_rate, float reverb_duration, rar_ring **out);
+RAR_API int rar_ring_destroy(rar_ring *ring);
+RAR_API int rar_ring_reset(rar_ring *ring);
+RAR_API int rar_ring_stop(rar_ring *ring);
+RAR_API int32_t rar_ring_size(const rar_ring *ring);
+RAR_API int32_t rar_ring_is_pinned(const rar_ring *ring);
+RAR_API int64_t rar_ring_frames_drained(const rar_ring *ring);
+RAR_API int rar_ring_push(rar_ring *ring, const float *samples, int32_t n, int64_t sample_offset);
+RAR_API int rar_ring_drain(rar_ring *ring, float *data, int32_t data_length, int32_t channels);
+RAR_API int rar_conv_process_to_ring(rar_convolver *conv, const float *in, rar_ring *const *rings, int64_t sample_offset);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 

@@ -103,6 +103,16 @@ SYMBOLS = {
     "rar_conv_process": (C.c_int, [_p, _p, _p]),
     "rar_conv_process_device": (C.c_int, [_p, _p, _p]),
     "rar_conv_bytes_per_block": (_i64, [_p]),
+    "rar_ring_create": (C.c_int, [_i32, _f32, C.POINTER(_p)]),
+    "rar_ring_destroy": (C.c_int, [_p]),
+    "rar_ring_reset": (C.c_int, [_p]),
+    "rar_ring_stop": (C.c_int, [_p]),
+    "rar_ring_size": (_i32, [_p]),
+    "rar_ring_is_pinned": (_i32, [_p]),
+    "rar_ring_frames_drained": (_i64, [_p]),
+    "rar_ring_push": (C.c_int, [_p, _p, _i32, _i64]),
+    "rar_ring_drain": (C.c_int, [_p, _p, _i32, _i32]),
+    "rar_conv_process_to_ring": (C.c_int, [_p, _p, _p, _i64]),
     "rar_device_info": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "rar_measure_fp32_peak": (C.c_int, [_p, C.POINTER(C.c_double)]),
     "rar_selftest_arithmetic": (C.c_int, [_p, _i64, C.c_uint32, C.POINTER(C.c_uint64)]),
@@ -376,6 +386,61 @@ class Context:
         return int(self._lib.rar_launch_count(self._h))
 
 
+class Ring:
+    """rar_ring*: AudioManager's playback ring, lock-free for one producer and one consumer thread.  Needs no GPU."""
+
+    def __init__(self, output_sample_rate: int = 48000, reverb_duration: float = 1.5):
+        self._lib = load()
+        h = _p()
+        rc = self._lib.rar_ring_create(output_sample_rate, reverb_duration, C.byref(h))
+        if rc < 0:
+            raise RarError(rc, "rar_ring_create failed")
+        self._h = h
+
+    def destroy(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.rar_ring_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.rar_ring_size(self._h))
+
+    @property
+    def pinned(self) -> bool:
+        return bool(self._lib.rar_ring_is_pinned(self._h))
+
+    @property
+    def frames_drained(self) -> int:
+        return int(self._lib.rar_ring_frames_drained(self._h))
+
+    def reset(self) -> None:
+        self._lib.rar_ring_reset(self._h)
+
+    def stop(self) -> None:
+        self._lib.rar_ring_stop(self._h)
+
+    def push(self, samples: np.ndarray, sample_offset: int) -> None:
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        rc = self._lib.rar_ring_push(self._h, a.ctypes.data if a.size else None, a.size, sample_offset)
+        if rc < 0:
+            raise RarError(rc, "rar_ring_push: bad arguments")
+
+    def drain(self, data: np.ndarray, channels: int = 1) -> None:
+        """OnAudioFilterRead(data, channels): fills data in place (float32, contiguous)."""
+        if data.dtype != np.float32 or not data.flags.c_contiguous:
+            raise ValueError("data must be a contiguous float32 array")
+        rc = self._lib.rar_ring_drain(self._h, data.ctypes.data if data.size else None, data.size, channels)
+        if rc < 0:
+            raise RarError(rc, "rar_ring_drain: bad arguments")
+
+
 def prepared_length(samples: int, clip_frequency: int, sample_rate: int) -> int:
     """rar_prepared_length: the length LoadSample produces (RayTraceManager.cs:150-153); host-only, needs no device."""
     return int(load().rar_prepared_length(samples, clip_frequency, sample_rate))
@@ -455,6 +520,14 @@ class Convolver:
 
     def process_device(self, d_in_ptr: int, d_out_ptr: int) -> None:
         self._ctx._ck(self._lib.rar_conv_process_device(self._h, _p(d_in_ptr), _p(d_out_ptr)))
+
+    def process_to_rings(self, block_in: np.ndarray, rings, sample_offset: int) -> None:
+        """rar_conv_process_to_ring: one block; stream s goes straight into rings[s] (None: dropped)."""
+        x = np.ascontiguousarray(block_in, dtype=np.float32)
+        if x.shape != (self.n_streams, self.block) or len(rings) != self.n_streams:
+            raise ValueError("one input row and one ring (or None) per stream")
+        arr = (_p * self.n_streams)(*[(r._h if r is not None else None) for r in rings])
+        self._ctx._ck(self._lib.rar_conv_process_to_ring(self._h, x.ctypes.data, arr, sample_offset))
 
     def bytes_per_block(self) -> int:
         return int(self._lib.rar_conv_bytes_per_block(self._h))

@@ -167,7 +167,7 @@ struct rar_convolver {
     PinnedBuf<float> h_ir;
     // batched response loads (rar_conv_set_irs*): device scratch for a group of responses, two pinned staging halves
     DevBuf<float> d_batch;
-    PinnedBuf<float> h_batch;
+    PinnedBuf<float> h_batch, h_out;
     cudaEvent_t batch_done[2] = {nullptr, nullptr};  // the staging half may be rewritten once its copy has completed
     // cross-faded impulse-response updates (allocated on first use)
     DevBuf<float2> H2, partial2;   // new spectra of the fading streams, their partial sums
@@ -1331,7 +1331,7 @@ int rar_conv_destroy(rar_convolver *cv) {
     cv->H.release(); cv->fdl.release(); cv->partial.release(); cv->prev.release();
     cv->d_in.release(); cv->d_out.release(); cv->d_irf.release(); cv->h_ir.release();
     cv->H2.release(); cv->partial2.release(); cv->d_fade.release(); cv->d_list.release();
-    cv->d_batch.release(); cv->h_batch.release();
+    cv->d_batch.release(); cv->h_batch.release(); cv->h_out.release();
     for (cudaEvent_t &e : cv->batch_done)
         if (e) cudaEventDestroy(e);
     delete cv;
@@ -1565,6 +1565,26 @@ int rar_conv_process(rar_convolver *cv, const float *in, float *out) {
     if (rc != RAR_OK) return rc;
     RAR_CUDA(ctx, cudaMemcpyAsync(out, cv->d_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RAR_OK;
+}
+
+int rar_conv_process_to_ring(rar_convolver *cv, const float *in, rar_ring *const *rings, int64_t sample_offset) {
+    if (!cv) return fail(nullptr, RAR_ERR_INVALID, "null convolver");
+    rar_context *ctx = cv->ctx;
+    RAR_ENTER(ctx);
+    if (!in || !rings || sample_offset < 0) return fail(ctx, RAR_ERR_INVALID, "null array or negative sample offset");
+    const size_t words = (size_t)cv->c.n_streams * cv->c.block;
+    RAR_CUDA(ctx, cv->h_out.reserve(words));   // pinned: the block lands next to the (pinned) rings without a bounce
+    RAR_CUDA(ctx, cudaMemcpyAsync(cv->d_in.p, in, words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = rar_conv_process_device(cv, cv->d_in.p, cv->d_out.p);
+    if (rc != RAR_OK) return rc;
+    RAR_CUDA(ctx, cudaMemcpyAsync(cv->h_out.p, cv->d_out.p, words * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int st = 0; st < cv->c.n_streams; st++) {
+        if (!rings[st]) continue;
+        rc = rar_ring_push(rings[st], cv->h_out.p + (size_t)st * cv->c.block, cv->c.block, sample_offset);
+        if (rc != RAR_OK) return fail(ctx, rc, "rar_ring_push failed");
+    }
     return RAR_OK;
 }
 

@@ -1,9 +1,12 @@
 """Host mirror of Assets/Script/AudioManager.cs: the playback sink of the streaming path.
 
 A lock-protected float ring buffer: `PushSamples` overlap-adds convolved chunks at an absolute sample
-offset (:45-54), `OnAudioFilterRead` (the audio thread in Unity) drains and zeroes it (:56-69).  This
-is CPU-side O(samples) glue and is not accelerated; it keeps the reference's API so that the
-manager code and the tests read like the reference.
+offset (:45-54), `OnAudioFilterRead` (the audio thread in Unity) drains and zeroes it (:56-69).  It keeps
+the reference's API so that the manager code and the tests read like the reference.
+
+`AudioManager` is the literal mirror (a Python lock, numpy arrays).  `NativeAudioManager` has the same
+interface over the library's lock-free single-producer / single-consumer ring (rar_ring_*, csrc/ring.cu):
+what the C# AudioManager binds so that the audio callback never waits for the main thread's push.
 """
 from __future__ import annotations
 
@@ -62,3 +65,44 @@ class AudioManager:
 
     def OnDestroy(self) -> None:                    # :71
         self.StopStreaming()
+
+
+class NativeAudioManager(AudioManager):
+    """AudioManager over the native lock-free ring (include/rar2d.h rar_ring_*)."""
+
+    def __init__(self, outputSampleRate: int = 48000, chunkDuration: float = 0.1):
+        super().__init__(outputSampleRate, chunkDuration)
+        self._ring = None
+
+    def StartStreaming(self, reverbDuration: float) -> None:
+        from .. import _capi
+        if self.isStreaming:
+            self.StopStreaming()
+        if self._ring is not None:
+            self._ring.destroy()
+        self._ring = _capi.Ring(self.sampleRate, reverbDuration)
+        self.bufferSize = self._ring.size
+        self.isStreaming = True
+
+    def StopStreaming(self) -> None:
+        if not self.isStreaming:
+            return
+        self.isStreaming = False
+        if self._ring is not None:
+            self._ring.stop()
+
+    def PushSamples(self, samples: np.ndarray, sampleOffset: int) -> None:
+        if not self.isStreaming or self._ring is None:
+            return
+        self._ring.push(samples, sampleOffset)
+
+    def OnAudioFilterRead(self, data: np.ndarray, channels: int) -> None:
+        if not self.isStreaming or self._ring is None:
+            return
+        self._ring.drain(data, channels)
+
+    def OnDestroy(self) -> None:
+        self.StopStreaming()
+        if self._ring is not None:
+            self._ring.destroy()
+            self._ring = None

@@ -271,3 +271,35 @@ def test_batched_response_load_equals_per_stream_loads(ctx, oracle):
     assert np.array_equal(irs, irs_after)
     want = oracle.convolve(x[5], irs[5] * np.float32(0.5), 1)[: 256 * 3]
     assert rel_l2(out[0][5], want) <= 1e-4
+
+
+def test_streaming_convolver_writes_straight_into_rings(ctx, oracle):
+    """rar_conv_process_to_ring: every block of stream s lands in rings[s] at its sample offset; draining the ring
+    gives the same samples rar_conv_process returns."""
+    rng = np.random.default_rng(21)
+    S, n, blocks = 3, 2000, 12
+    irs = (rng.standard_normal((S, n)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (S, 256 * blocks)).astype(np.float32)
+    outs = []
+    for to_ring in (False, True):
+        cv = _capi.Convolver(ctx, S, 256, n)
+        rings = [_capi.Ring(48000, 0.5), None, _capi.Ring(48000, 0.5)]
+        try:
+            cv.set_irs(0, irs)
+            if to_ring:
+                for k in range(blocks):
+                    cv.process_to_rings(x[:, k * 256:(k + 1) * 256], rings, k * 256)
+                y = np.zeros((S, 256 * blocks), np.float32)
+                for s in (0, 2):
+                    rings[s].drain(y[s], 1)
+                assert rings[0].pinned
+            else:
+                y = np.concatenate([cv.process(x[:, k * 256:(k + 1) * 256]) for k in range(blocks)], axis=1)
+            outs.append(y)
+        finally:
+            cv.destroy()
+            for r in rings:
+                if r is not None:
+                    r.destroy()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][2], outs[1][2]) and not outs[1][1].any()
+    assert rel_l2(outs[1][2], oracle.convolve(x[2], irs[2], 1)[: 256 * blocks]) <= 1e-4
