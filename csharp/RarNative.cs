@@ -121,6 +121,7 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_device_info(IntPtr ctx, out int smCount, out int smClockKhz, out int smemOptinBytes);
         [DllImport(Lib)] public static extern int rar_measure_fp32_peak(IntPtr ctx, out double laneOpsPerSecond);
         [DllImport(Lib)] public static extern int rar_selftest_arithmetic(IntPtr ctx, long nSamples, uint seed, [Out] ulong[] mismatches5);
+        [DllImport(Lib)] public static extern int rar_debug_grid(IntPtr ctx, out int nx, out int ny, out long nItems, out ulong digest);
         [DllImport(Lib)] public static extern long rar_launch_count(IntPtr ctx);
 
         public static string LastError(IntPtr ctx) => Marshal.PtrToStringAnsi(rar_last_error(ctx));

@@ -414,6 +414,11 @@ RAR_API int rar_measure_fp32_peak(rar_context *ctx, double *lane_ops_per_s);
  * division by a launch-invariant divisor, range test).  All zeros is the only passing result.  Blocking. */
 RAR_API int rar_selftest_arithmetic(rar_context *ctx, int64_t n_samples, uint32_t seed, uint64_t *mismatches);
 
+/* Test hook for the uniform grid of RAR_FLAG_USE_GRID: builds it for the current walls if necessary (on the device,
+ * asynchronously, as a grid trace would) and returns its dimensions, the total length of its cell lists and a digest
+ * of them, so that a test can hold the device-built grid against the host builder's.  Blocking. */
+RAR_API int rar_debug_grid(rar_context *ctx, int32_t *nx, int32_t *ny, int64_t *n_items, uint64_t *digest);
+
 /* Number of kernels this library has launched on the context since creation (bench: gpu_launches). */
 RAR_API int64_t rar_launch_count(const rar_context *ctx);
 

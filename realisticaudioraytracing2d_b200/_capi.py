@@ -116,6 +116,7 @@ SYMBOLS = {
     "rar_device_info": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "rar_measure_fp32_peak": (C.c_int, [_p, C.POINTER(C.c_double)]),
     "rar_selftest_arithmetic": (C.c_int, [_p, _i64, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "rar_debug_grid": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(C.c_uint64)]),
     "rar_launch_count": (_i64, [_p]),
 }
 
@@ -381,6 +382,12 @@ class Context:
         m = (C.c_uint64 * 5)()
         self._ck(self._lib.rar_selftest_arithmetic(self._h, n_samples, seed & 0xFFFFFFFF, m))
         return [int(v) for v in m]
+
+    def debug_grid(self) -> dict:
+        """rar_debug_grid: dimensions, list length and digest of the (device-built) uniform grid of the current walls."""
+        nx, ny, n, d = _i32(), _i32(), _i64(), C.c_uint64()
+        self._ck(self._lib.rar_debug_grid(self._h, C.byref(nx), C.byref(ny), C.byref(n), C.byref(d)))
+        return {"nx": nx.value, "ny": ny.value, "n_items": n.value, "digest": d.value}
 
     def launch_count(self) -> int:
         return int(self._lib.rar_launch_count(self._h))

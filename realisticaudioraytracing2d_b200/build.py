@@ -27,6 +27,7 @@ UNITS = [
     ("exchange_kernel.cu", []),
     ("clip_kernel.cu", ["--fmad=false", "-prec-div=true", "-ftz=false"]),
     ("ring.cu", []),
+    ("grid_kernel.cu", ["--fmad=false"]),
     ("rar2d_api.cu", []),
 ]
 HEADERS = ["rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_layout.h", "rar_internal.h", "../../include/rar2d.h"]

@@ -489,7 +489,7 @@ inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per);
 
 }  // namespace
 
-void conv_init_tables() {
+void conv_init_tables(cudaStream_t stream) {
     static std::mutex mu;
     static bool done[64] = {false};
     int dev = 0;
@@ -501,8 +501,11 @@ void conv_init_tables() {
     for (int k = 0; k < kFftM; k++) tw[k] = f2{(float)cos(two_pi * k / kFftM), (float)-sin(two_pi * k / kFftM)};
     for (int k = 0; k <= kFftM / 2; k++)
         tw2[k] = f2{(float)cos(two_pi * k / (2 * kFftM)), (float)-sin(two_pi * k / (2 * kFftM))};
-    cudaMemcpyToSymbol(g_tw, tw, sizeof tw);
-    cudaMemcpyToSymbol(g_tw2, tw2, sizeof tw2);
+    // on the caller's stream (the context streams are non-blocking: nothing orders them against the legacy stream);
+    // the host arrays are on this stack frame, so the copies are awaited before returning
+    cudaMemcpyToSymbolAsync(g_tw, tw, sizeof tw, 0, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyToSymbolAsync(g_tw2, tw2, sizeof tw2, 0, cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);
     if (dev >= 0 && dev < 64) done[dev] = true;
 }
 

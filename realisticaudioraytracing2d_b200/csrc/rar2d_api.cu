@@ -128,12 +128,19 @@ struct rar_context {
     DevBuf<float> d_band_abs;
     int n_walls = -1;  // -1: never set
     int band_rows = 0, band_count = 0;
-    PinnedBuf<f4> h_planes;            // pinned staging of the geo | mat0 | mat1 planes of one upload
+    DevBuf<f2> d_end;                  // wall end points (the grid builder needs them unrounded)
+    PinnedBuf<f4> h_planes;            // pinned staging of the geo | mat0 | mat1 | end planes of one upload
     cudaEvent_t walls_uploaded = nullptr;  // the staging buffer may be rewritten once this has completed
+    PinnedBuf<float> h_bands;          // pinned staging of the band-absorption table
+    cudaEvent_t bands_uploaded = nullptr;
+    PinnedBuf<unsigned char> h_listeners;  // pinned staging of rar_trace_listeners' positions and slot addresses
+    cudaEvent_t listeners_uploaded = nullptr;
     std::vector<rar_segment> h_walls;  // kept for the lazy grid build
-    GridHost h_grid;
-    DevBuf<uint32_t> d_grid_start, d_grid_items;
+    GridFrame grid_frame_;             // frame of the current grid (nx == 0: none could be built)
+    GridHost h_grid;                   // host-built lists (fallback for scenes whose registration bound is enormous)
+    DevBuf<uint32_t> d_grid_start, d_grid_items, d_grid_cnt;
     DevBuf<f4> d_grid_geo;
+    long long grid_items_bound = 0;
     bool grid_valid = false;
     bool walls_are_opaque = false;  // no wall has transmission > 0
     bool walls_are_bounded = false; // every coordinate finite and within 2^30 (rar_layout.h walls_bounded)
@@ -226,30 +233,49 @@ int check_trace_params(rar_context *ctx, const rar_trace_params *p) {
     return RAR_OK;
 }
 
-// Builds (once per wall upload) and attaches the uniform grid when the call asks for it.
+// Builds (once per wall upload) and attaches the uniform grid when the call asks for it.  The lists are built on the
+// device by kernels enqueued on the context's stream (grid_kernel.cu); the host computes the frame and an upper
+// bound of the list length in one pass over the walls and waits for nothing.
+constexpr long long kGridDeviceBuildMaxItems = 64LL << 20;
+
 int attach_grid(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     a.use_grid = 0;
     if (!(p->flags & RAR_FLAG_USE_GRID) || ctx->n_walls <= 0) return RAR_OK;
     if (!ctx->grid_valid) {
-        build_grid(ctx->h_walls.data(), ctx->n_walls, ctx->h_grid);
-        const GridHost &g = ctx->h_grid;
-        if (g.nx > 0) {
-            RAR_CUDA(ctx, ctx->d_grid_start.reserve(g.cell_start.size()));
-            RAR_CUDA(ctx, ctx->d_grid_items.reserve(g.items.size() + 1));
-            RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_start.p, g.cell_start.data(), g.cell_start.size() * sizeof(uint32_t),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-            RAR_CUDA(ctx, ctx->d_grid_geo.reserve(g.items.size() + 1));
-            if (!g.items.empty()) {
-                RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_items.p, g.items.data(), g.items.size() * sizeof(uint32_t),
+        long long bound = 0;
+        ctx->grid_frame_ = grid_frame(ctx->h_walls.data(), ctx->n_walls, &bound);
+        const GridFrame &fr = ctx->grid_frame_;
+        if (fr.nx > 0) {
+            const size_t n_cells = (size_t)fr.nx * fr.ny;
+            RAR_CUDA(ctx, ctx->d_grid_start.reserve(n_cells + 1));
+            if (bound <= kGridDeviceBuildMaxItems) {
+                RAR_CUDA(ctx, ctx->d_grid_cnt.reserve(n_cells));
+                RAR_CUDA(ctx, ctx->d_grid_items.reserve((size_t)bound + 1));
+                RAR_CUDA(ctx, ctx->d_grid_geo.reserve((size_t)bound + 1));
+                RAR_CUDA(ctx, launch_grid_build(ctx->d_geo.p, ctx->d_end.p, ctx->n_walls, fr, ctx->d_grid_cnt.p, ctx->d_grid_start.p,
+                                                ctx->d_grid_items.p, ctx->d_grid_geo.p, ctx->stream));
+                ctx->launches += 4;
+            } else {
+                // a scene of thousands of walls that each span the whole extent: build on the host (blocking)
+                build_grid(ctx->h_walls.data(), ctx->n_walls, ctx->h_grid);
+                const GridHost &g = ctx->h_grid;
+                RAR_CUDA(ctx, ctx->d_grid_items.reserve(g.items.size() + 1));
+                RAR_CUDA(ctx, ctx->d_grid_geo.reserve(g.items.size() + 1));
+                RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_start.p, g.cell_start.data(), g.cell_start.size() * sizeof(uint32_t),
                                               cudaMemcpyHostToDevice, ctx->stream));
-                RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_geo.p, g.item_geo.data(), g.items.size() * sizeof(f4),
-                                              cudaMemcpyHostToDevice, ctx->stream));
+                if (!g.items.empty()) {
+                    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_items.p, g.items.data(), g.items.size() * sizeof(uint32_t),
+                                                  cudaMemcpyHostToDevice, ctx->stream));
+                    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_geo.p, g.item_geo.data(), g.items.size() * sizeof(f4),
+                                                  cudaMemcpyHostToDevice, ctx->stream));
+                }
+                RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             }
-            RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
+        ctx->grid_items_bound = bound;
         ctx->grid_valid = true;
     }
-    const GridHost &g = ctx->h_grid;
+    const GridFrame &g = ctx->grid_frame_;
     if (g.nx <= 0) return RAR_OK;  // no grid could be built (non-finite coordinates): brute force
     a.grid.x0 = g.x0;
     a.grid.y0 = g.y0;
@@ -431,9 +457,10 @@ int rar_create(int device, rar_context **out) {
     }
     ctx->stream = ctx->own_stream;
     ctx->slots.resize(2);  // ping / pong, RayTraceManager.cs:36
-    conv_init_tables();
+    conv_init_tables(ctx->own_stream);
     e = ctx->d_counters.reserve(8);
-    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);  // creation-time initialisation is complete on return
     if (e != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
@@ -457,7 +484,13 @@ int rar_destroy(rar_context *ctx) {
         if (s.d_H) cudaFree(s.d_H);
     }
     ctx->h_planes.release();
+    ctx->h_bands.release();
+    ctx->h_listeners.release();
+    ctx->d_end.release();
+    ctx->d_grid_cnt.release();
     if (ctx->walls_uploaded) cudaEventDestroy(ctx->walls_uploaded);
+    if (ctx->bands_uploaded) cudaEventDestroy(ctx->bands_uploaded);
+    if (ctx->listeners_uploaded) cudaEventDestroy(ctx->listeners_uploaded);
     ctx->d_geo.release();
     ctx->d_mat0.release();
     ctx->d_mat1.release();
@@ -504,23 +537,27 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
     static_assert(sizeof(rar_segment) == 40, "Segment must be 40 bytes (Helpers/SceneHelper.cs:15-22)");
     static_assert(sizeof(rar_ray_info) == 16, "RayInfo must be 16 bytes (RayTraceManager.cs:43)");
     const size_t pad = ((size_t)n + 2 + 1) & ~(size_t)1;  // mat1 plane is bulk-copied in 16-byte units; even => planes stay 16-byte aligned
-    // Pinned staging: the three planes go up as asynchronous copies and the call returns without waiting for
+    // Pinned staging: the planes go up as asynchronous copies and the call returns without waiting for
     // them; the next upload waits (normally not at all) for this one before it rewrites the staging buffer.
     if (ctx->walls_uploaded) RAR_CUDA(ctx, cudaEventSynchronize(ctx->walls_uploaded));
     else RAR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->walls_uploaded, cudaEventDisableTiming));
     if (pad * 3 > ctx->h_planes.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // reallocation frees the old buffer
-    RAR_CUDA(ctx, ctx->h_planes.reserve(pad * 3));
+    RAR_CUDA(ctx, ctx->h_planes.reserve(pad * 3));   // geo | mat0 | (mat1, end): two 8-byte planes share the third f4 plane
     f4 *h_geo = ctx->h_planes.p, *h_mat0 = h_geo + pad;
     f2 *h_mat1 = reinterpret_cast<f2 *>(h_mat0 + pad);
-    std::memset(h_geo, 0, pad * (2 * sizeof(f4) + sizeof(f2)));
+    f2 *h_end = h_mat1 + pad;
+    std::memset(h_geo, 0, pad * 3 * sizeof(f4));
     split_walls(segments, n, h_geo, h_mat0, h_mat1);
+    for (int w = 0; w < n; w++) h_end[w] = f2{segments[w].end[0], segments[w].end[1]};
     RAR_CUDA(ctx, ctx->d_geo.reserve(pad));
     RAR_CUDA(ctx, ctx->d_mat0.reserve(pad));
     RAR_CUDA(ctx, ctx->d_mat1.reserve(pad));
+    RAR_CUDA(ctx, ctx->d_end.reserve(pad));
     // The previous planes may still be read by an enqueued trace; stream order makes the copies safe.
     RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_geo.p, h_geo, pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
     RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat0.p, h_mat0, pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
     RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat1.p, h_mat1, pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_end.p, h_end, pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
     RAR_CUDA(ctx, cudaEventRecord(ctx->walls_uploaded, ctx->stream));
     if (n != ctx->n_walls) {
         ctx->band_rows = 0;
@@ -540,9 +577,19 @@ int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int3
     if (n != ctx->n_walls) return fail(ctx, RAR_ERR_INVALID, "row count must equal the wall count");
     if (bands < 2 || bands > 128) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 2..128");
     if (n > 0 && !absorption) return fail(ctx, RAR_ERR_INVALID, "null absorption table");
-    RAR_CUDA(ctx, ctx->d_band_abs.reserve((size_t)n * bands + 16));  // a short last chunk of 8 reads past its row
-    if (n > 0)
-        RAR_CUDA(ctx, cudaMemcpy(ctx->d_band_abs.p, absorption, (size_t)n * bands * sizeof(float), cudaMemcpyHostToDevice));
+    // Staged through pinned memory and copied on the context's stream: ordered behind any banded trace still in
+    // flight (which reads the old table) and ahead of the next one, without blocking the caller.
+    const size_t words = (size_t)n * bands;
+    if (ctx->bands_uploaded) RAR_CUDA(ctx, cudaEventSynchronize(ctx->bands_uploaded));
+    else RAR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bands_uploaded, cudaEventDisableTiming));
+    if (words + 16 > ctx->d_band_abs.cap || words > ctx->h_bands.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // growth frees buffers in use
+    RAR_CUDA(ctx, ctx->d_band_abs.reserve(words + 16));  // a short last chunk of 8 reads past its row
+    RAR_CUDA(ctx, ctx->h_bands.reserve(words + 1));
+    if (n > 0) {
+        std::memcpy(ctx->h_bands.p, absorption, words * sizeof(float));
+        RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_band_abs.p, ctx->h_bands.p, words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        RAR_CUDA(ctx, cudaEventRecord(ctx->bands_uploaded, ctx->stream));
+    }
     ctx->band_rows = n;
     ctx->band_count = bands;
     return RAR_OK;
@@ -1092,12 +1139,20 @@ int rar_trace_listeners(rar_context *ctx, const rar_trace_params *params, const 
         pos[l] = f2{listeners_xy[2 * l], listeners_xy[2 * l + 1]};
         S->H_valid = false;
     }
+    // positions and slot addresses go up through pinned staging on the context's stream; the call does not wait for them
+    const size_t pos_bytes = (size_t)n_listeners * sizeof(f2), hist_bytes = (size_t)n_listeners * sizeof(unsigned long long *);
+    if (ctx->listeners_uploaded) RAR_CUDA(ctx, cudaEventSynchronize(ctx->listeners_uploaded));
+    else RAR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->listeners_uploaded, cudaEventDisableTiming));
+    if ((size_t)n_listeners > ctx->d_listeners.cap || (size_t)n_listeners > ctx->d_listener_hists.cap)
+        RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // growth frees arrays an enqueued launch may still read
     RAR_CUDA(ctx, ctx->d_listeners.reserve((size_t)n_listeners));
     RAR_CUDA(ctx, ctx->d_listener_hists.reserve((size_t)n_listeners));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners.p, pos.data(), (size_t)n_listeners * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_listener_hists.p, hists.data(), (size_t)n_listeners * sizeof(unsigned long long *),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors are pageable
+    RAR_CUDA(ctx, ctx->h_listeners.reserve(pos_bytes + hist_bytes));
+    std::memcpy(ctx->h_listeners.p, hists.data(), hist_bytes);              // 8-byte items first: keeps both parts aligned
+    std::memcpy(ctx->h_listeners.p + hist_bytes, pos.data(), pos_bytes);
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_listener_hists.p, ctx->h_listeners.p, hist_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_listeners.p, ctx->h_listeners.p + hist_bytes, pos_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaEventRecord(ctx->listeners_uploaded, ctx->stream));
     TraceLaunch a;
     fill_launch(ctx, params, a);
     rc = attach_grid(ctx, params, a);
@@ -1635,6 +1690,33 @@ int rar_measure_fp32_peak(rar_context *ctx, double *lane_ops_per_s) {
     RAR_CUDA(ctx, e);
     const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
     *lane_ops_per_s = ops / (best_ms * 1e-3);
+    return RAR_OK;
+}
+
+int rar_debug_grid(rar_context *ctx, int32_t *nx, int32_t *ny, int64_t *n_items, uint64_t *digest) {
+    RAR_ENTER(ctx);
+    if (ctx->n_walls < 0) return fail(ctx, RAR_ERR_STATE, "rar_set_walls has not been called");
+    rar_trace_params p;
+    std::memset(&p, 0, sizeof p);
+    p.flags = RAR_FLAG_USE_GRID;
+    TraceLaunch a;
+    std::memset(&a, 0, sizeof a);
+    int rc = attach_grid(ctx, &p, a);
+    if (rc != RAR_OK) return rc;
+    const GridFrame &g = ctx->grid_frame_;
+    if (nx) *nx = g.nx;
+    if (ny) *ny = g.ny;
+    if (n_items) *n_items = 0;
+    if (digest) *digest = 0;
+    if (!a.use_grid) return RAR_OK;
+    const size_t n_cells = (size_t)g.nx * g.ny;
+    std::vector<uint32_t> start(n_cells + 1);
+    RAR_CUDA(ctx, cudaMemcpyAsync(start.data(), ctx->d_grid_start.p, (n_cells + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> items(start[n_cells]);
+    if (!items.empty()) RAR_CUDA(ctx, cudaMemcpy(items.data(), ctx->d_grid_items.p, items.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (n_items) *n_items = (int64_t)items.size();
+    if (digest) *digest = grid_digest(start.data(), start.size(), items.data(), items.size());
     return RAR_OK;
 }
 

@@ -154,6 +154,11 @@ struct ClipPrep {
 };
 cudaError_t launch_prepare_clips(const ClipPrep &a, cudaStream_t s, int sm_count);
 
-void conv_init_tables();  // uploads twiddle tables to constant memory of the current device (idempotent per device)
+void conv_init_tables(cudaStream_t s);  // uploads the twiddle tables of the current device on stream s (idempotent per device)
+
+// grid_kernel.cu -- device build of the uniform grid's lists (count, scan, fill, finish); cnt holds nx*ny words
+struct GridFrame;
+cudaError_t launch_grid_build(const f4 *geo, const f2 *end, int n, const GridFrame &fr, unsigned *cnt, unsigned *cell_start,
+                              unsigned *items, f4 *item_geo, cudaStream_t s);
 
 }  // namespace rar

@@ -81,6 +81,42 @@ inline RayConsts ray_consts(const rar_trace_params &p) {
 // Uniform grid over the walls for RAR_FLAG_USE_GRID (see rar_ray.cuh GridView).  Conservative by construction:
 // a wall is registered in every cell whose box, grown by the margin m, meets the wall's supporting strip
 // (separating-axis test on the wall's normal, inside the wall's bounding box grown by m).
+//
+// The frame (extent, cell size, margin) is computed on the host in one pass over the walls; which cells a wall is
+// registered in is decided by wall_cell_box / wall_in_cell, plain IEEE double arithmetic shared by the host builder
+// below (tests, host emulation) and the device builder (grid_kernel.cu, compiled without FMA contraction), so both
+// produce the same lists.
+struct GridFrame {
+    float x0 = 0, y0 = 0, cw = 1, ch = 1;  // the float-rounded frame the ray kernels walk
+    int nx = 0, ny = 0;
+    double m = 0;                          // registration margin
+};
+
+// Cell index range of the wall's bounding box grown by the margin, clipped to the grid.
+RAR_HD void wall_cell_box(const GridFrame &g, double ax, double ay, double bx, double by, int &ix0, int &ix1, int &iy0, int &iy1) {
+    const double fx0 = g.x0, fy0 = g.y0, fcw = g.cw, fch = g.ch;
+    const double lox = ax < bx ? ax : bx, hix = ax < bx ? bx : ax, loy = ay < by ? ay : by, hiy = ay < by ? by : ay;
+    ix0 = (int)floor((lox - g.m - fx0) / fcw);
+    ix1 = (int)floor((hix + g.m - fx0) / fcw);
+    iy0 = (int)floor((loy - g.m - fy0) / fch);
+    iy1 = (int)floor((hiy + g.m - fy0) / fch);
+    ix0 = ix0 > 0 ? ix0 : 0;
+    iy0 = iy0 > 0 ? iy0 : 0;
+    ix1 = ix1 < g.nx - 1 ? ix1 : g.nx - 1;
+    iy1 = iy1 < g.ny - 1 ? iy1 : g.ny - 1;
+}
+
+// Does the wall's supporting strip meet cell (ix, iy) grown by the margin?
+RAR_HD bool wall_in_cell(const GridFrame &g, double ax, double ay, double bx, double by, int ix, int iy) {
+    const double fx0 = g.x0, fy0 = g.y0, fcw = g.cw, fch = g.ch;
+    const double vx = bx - ax, vy = by - ay;
+    const double hx = 0.5 * fcw + g.m, hy = 0.5 * fch + g.m;
+    const double reach = fabs(vy) * hx + fabs(vx) * hy;
+    const double cx = fx0 + (ix + 0.5) * fcw, cy = fy0 + (iy + 0.5) * fch;
+    const double dist = fabs(vx * (cy - ay) - vy * (cx - ax));
+    return !(dist > reach * (1.0 + 1e-9) + 1e-300);
+}
+
 struct GridHost {
     float x0 = 0, y0 = 0, cw = 1, ch = 1;
     int nx = 0, ny = 0;
@@ -88,14 +124,17 @@ struct GridHost {
     std::vector<f4> item_geo;  // endpoint record of items[i], so a cell's walls are one contiguous read
 };
 
-inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
-    g = GridHost();
-    if (n <= 0) return;
+// The frame for a wall set; nx == 0 when no grid can be built (no walls, non-finite coordinates: brute force handles
+// those).  *bound receives an upper bound of the number of (cell, wall) registrations: the cells of every wall's box.
+inline GridFrame grid_frame(const rar_segment *walls, int n, long long *bound = nullptr) {
+    GridFrame g;
+    if (bound) *bound = 0;
+    if (n <= 0) return g;
     double minx = 1e300, miny = 1e300, maxx = -1e300, maxy = -1e300, maxabs = 0;
     for (int w = 0; w < n; w++) {
         for (int e = 0; e < 2; e++) {
             const double x = e ? walls[w].end[0] : walls[w].start[0], y = e ? walls[w].end[1] : walls[w].start[1];
-            if (!(std::isfinite(x) && std::isfinite(y))) return;  // no grid for non-finite scenes: brute force handles them
+            if (!(std::isfinite(x) && std::isfinite(y))) return g;
             minx = std::min(minx, x); maxx = std::max(maxx, x);
             miny = std::min(miny, y); maxy = std::max(maxy, y);
             maxabs = std::max(maxabs, std::max(std::fabs(x), std::fabs(y)));
@@ -111,25 +150,33 @@ inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
     const int ny = (int)std::min(2048.0, std::max(1.0, std::ceil(ey / cell)));
     const double cw = ex / nx, ch = ey / ny;
     const double ulp = std::ldexp(std::max(maxabs, 1e-30), -23);
-    const double m = std::max(0.02 * std::min(cw, ch), 128.0 * ulp);
+    g.m = std::max(0.02 * std::min(cw, ch), 128.0 * ulp);
     g.x0 = (float)minx; g.y0 = (float)miny; g.cw = (float)cw; g.ch = (float)ch; g.nx = nx; g.ny = ny;
-    // use the float-rounded frame the device will use
-    const double fx0 = g.x0, fy0 = g.y0, fcw = g.cw, fch = g.ch;
+    if (bound) {
+        for (int w = 0; w < n; w++) {
+            int ix0, ix1, iy0, iy1;
+            wall_cell_box(g, walls[w].start[0], walls[w].start[1], walls[w].end[0], walls[w].end[1], ix0, ix1, iy0, iy1);
+            if (ix1 >= ix0 && iy1 >= iy0) *bound += (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+        }
+    }
+    return g;
+}
+
+inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
+    g = GridHost();
+    const GridFrame fr = grid_frame(walls, n);
+    if (fr.nx <= 0) return;
+    const int nx = fr.nx, ny = fr.ny;
+    g.x0 = fr.x0; g.y0 = fr.y0; g.cw = fr.cw; g.ch = fr.ch; g.nx = nx; g.ny = ny;
     std::vector<uint32_t> count((size_t)nx * ny + 1, 0);
     for (int pass = 0; pass < 2; pass++) {
         for (int w = 0; w < n; w++) {
             const double ax = walls[w].start[0], ay = walls[w].start[1], bx = walls[w].end[0], by = walls[w].end[1];
-            const double vx = bx - ax, vy = by - ay;
-            int ix0 = (int)std::floor((std::min(ax, bx) - m - fx0) / fcw), ix1 = (int)std::floor((std::max(ax, bx) + m - fx0) / fcw);
-            int iy0 = (int)std::floor((std::min(ay, by) - m - fy0) / fch), iy1 = (int)std::floor((std::max(ay, by) + m - fy0) / fch);
-            ix0 = std::max(ix0, 0); iy0 = std::max(iy0, 0); ix1 = std::min(ix1, nx - 1); iy1 = std::min(iy1, ny - 1);
-            const double hx = 0.5 * fcw + m, hy = 0.5 * fch + m;
-            const double reach = std::fabs(vy) * hx + std::fabs(vx) * hy;
+            int ix0, ix1, iy0, iy1;
+            wall_cell_box(fr, ax, ay, bx, by, ix0, ix1, iy0, iy1);
             for (int iy = iy0; iy <= iy1; iy++) {
                 for (int ix = ix0; ix <= ix1; ix++) {
-                    const double cx = fx0 + (ix + 0.5) * fcw, cy = fy0 + (iy + 0.5) * fch;
-                    const double dist = std::fabs(vx * (cy - ay) - vy * (cx - ax));
-                    if (dist > reach * (1.0 + 1e-9) + 1e-300) continue;
+                    if (!wall_in_cell(fr, ax, ay, bx, by, ix, iy)) continue;
                     const size_t cell_id = (size_t)iy * nx + ix;
                     if (pass == 0) count[cell_id + 1]++;
                     else g.items[g.cell_start[cell_id] + count[cell_id]++] = (uint32_t)w;
@@ -152,6 +199,14 @@ inline void build_grid(const rar_segment *walls, int n, GridHost &g) {
             std::fill(count.begin(), count.end(), 0);
         }
     }
+}
+
+// FNV-style digest of a grid's lists (tests: the device-built grid equals the host-built one).
+inline uint64_t grid_digest(const uint32_t *cell_start, size_t n_cells_plus_1, const uint32_t *items, size_t n_items) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n_cells_plus_1; i++) h = (h ^ cell_start[i]) * 1099511628211ull;
+    for (size_t i = 0; i < n_items; i++) h = (h ^ items[i]) * 1099511628211ull;
+    return h;
 }
 
 // Thread-id range a trace call covers: the reference dispatches ceil(rayCount/64) groups of 64 threads

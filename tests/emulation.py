@@ -90,3 +90,11 @@ def intersect_many(rays, segs, closest):
     lib().emu_intersect_many(C.c_void_p(rays.ctypes.data), C.c_void_p(segs.ctypes.data), C.c_void_p(closest.ctypes.data),
                              len(rays), C.c_void_p(out.ctypes.data))
     return out
+
+
+def grid_digest(walls):
+    """Dimensions, list length and digest of the HOST-built uniform grid (rar_layout.h build_grid)."""
+    walls = np.ascontiguousarray(walls)
+    nx, ny, n, d = C.c_int(), C.c_int(), C.c_longlong(), C.c_ulonglong()
+    lib().emu_grid_digest(C.c_void_p(walls.ctypes.data if len(walls) else None), len(walls), C.byref(nx), C.byref(ny), C.byref(n), C.byref(d))
+    return {"nx": nx.value, "ny": ny.value, "n_items": n.value, "digest": d.value}

@@ -138,6 +138,16 @@ int emu_trace_nocount(const rar_segment *walls, int n, const float *band_abs, co
     return emu_trace_impl(false, walls, n, band_abs, p, hist, hits, cap, count, out);
 }
 
+// Digest of the host-built uniform grid (the device builder must produce the same lists).
+extern "C" __attribute__((visibility("default")))
+int emu_grid_digest(const rar_segment *walls, int n, int *nx, int *ny, long long *n_items, unsigned long long *digest) {
+    rar::GridHost g;
+    rar::build_grid(walls, n, g);
+    *nx = g.nx; *ny = g.ny; *n_items = (long long)g.items.size();
+    *digest = g.nx > 0 ? rar::grid_digest(g.cell_start.data(), g.cell_start.size(), g.items.data(), g.items.size()) : 0;
+    return 0;
+}
+
 // ---- FFT / partitioned overlap-save convolution: the same index logic as conv_kernels.cu ----------------
 #include <cmath>
 #include "../realisticaudioraytracing2d_b200/csrc/rar_fft.cuh"
