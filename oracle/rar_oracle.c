@@ -46,6 +46,30 @@
 
 #define ORC_API __attribute__((visibility("default")))
 
+/* ---- the contract-sensitivity variant (tests only) --------------------------------------------------------------
+ * Built with -DORC_VARIANT_NAIVE (oracle/Makefile target `naive`) this same file becomes a second oracle that makes
+ * the OTHER defensible reading of every point where the arithmetic contract had to choose, i.e. what a different
+ * HLSL compiler might legitimately have emitted:
+ *   - no fused multiply-add anywhere: fmaf(a,b,c) := (a*b) + c with two roundings;
+ *   - sin / cos / asin from libm instead of the fixed polynomial kernels;
+ *   - vector / scalar as true divisions instead of one reciprocal and multiplies (normalize, checkVis direction,
+ *     toList / distList, the 1 / totalD^2 factor).
+ * tests/test_oracle_sensitivity.py traces the bundled rooms and the shoebox with both and shows that the impulse
+ * responses differ by far less than the frame-to-frame Monte-Carlo spread of either: the unpinned choices of the
+ * contract do not move the result a listener hears. */
+#ifdef ORC_VARIANT_NAIVE
+#undef fmaf
+#define fmaf(a, b, c) orc_naive_fma((a), (b), (c))
+static inline float orc_naive_fma(float a, float b, float c) {
+    volatile float p = a * b; /* rounded product, then a rounded sum */
+    return p + c;
+}
+/* x / s for a component x of a vector divided by the scalar s (inv = 1/s is the contract's reading) */
+#define ORC_VDIV(x, s, inv) ((x) / (s))
+#else
+#define ORC_VDIV(x, s, inv) ((x) * (inv))
+#endif
+
 /* Common.hlsl:4-6 */
 static const float ORC_EPS = 1e-4f;
 static const float ORC_INF = 1e8f;
@@ -150,6 +174,11 @@ ORC_API int orc_refract(float ix, float iy, float nx, float ny, float eta, float
  * any IEEE machine), 3-term Cody-Waite reduction by pi/2, then the classic single-precision minimax
  * polynomials on [-pi/4, pi/4]. */
 ORC_API void orc_sincosf(float x, float *sn, float *cs) {
+#ifdef ORC_VARIANT_NAIVE
+    *sn = sinf(x);
+    *cs = cosf(x);
+    return;
+#endif
     const float TWO_OVER_PI = 0.636619772f;
     const float MAGIC = 12582912.0f; /* 1.5 * 2^23 */
     float kf = fmaf(x, TWO_OVER_PI, MAGIC) - MAGIC;
@@ -174,6 +203,9 @@ ORC_API void orc_sincosf(float x, float *sn, float *cs) {
 
 /* asin on [-1,1] (inputs outside are clamped): polynomial for |x|<=0.5, half-angle identity above. */
 ORC_API float orc_asinf(float x) {
+#ifdef ORC_VARIANT_NAIVE
+    return asinf(x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x));
+#endif
     float a = fabsf(x);
     if (a > 1.0f) a = 1.0f;
     int big = a > 0.5f;
@@ -244,7 +276,7 @@ static void emit(const trace_env *env, uint32_t ray, int bounce, int kind, float
 /* Raytrace2D.compute:40-47 */
 static int check_vis(const trace_env *env, float sx, float sy, float ex, float ey, float dist, orc_counters *ctr) {
     float inv_dist = 1.0f / dist; /* (end - start) / dist as vector * (1/scalar) */
-    float dx = (ex - sx) * inv_dist, dy = (ey - sy) * inv_dist;
+    float dx = ORC_VDIV(ex - sx, dist, inv_dist), dy = ORC_VDIV(ey - sy, dist, inv_dist);
     float lim = dist - 0.1f;
     for (int w = 0; w < env->n_walls; w++) {
         const orc_segment *s = &env->walls[w];
@@ -315,14 +347,14 @@ static void trace_one(const trace_env *env, uint32_t id, orc_counters *ctr) {
                 int flip = dot2(dirx, diry, wall->nx, wall->ny) > 0.0f;
                 float enx = flip ? -wall->nx : wall->nx, eny = flip ? -wall->ny : wall->ny;
                 float inv_dl = 1.0f / dl; /* toList / distList as vector * (1/scalar) */
-                float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
+                float cos_t = fmaxf(0.0f, dot2(enx, eny, ORC_VDIV(tlx, dl, inv_dl), ORC_VDIV(tly, dl, inv_dl)));
                 float total = dist + dl;
                 float geo = (cos_t * 0.5f);
                 float inv = 1.0f / (total * total);
-                float contrib = ((energy * keep) * geo) * inv;
+                float contrib = ORC_VDIV((energy * keep) * geo, total * total, inv);
                 if (contrib > 1e-5f) {
                     float t = time + dl / p->speed_of_sound;
-                    for (int b = 0; b < nb; b++) band_out[b] = ((band_e[b] * (1.0f - wabs[b])) * geo) * inv;
+                    for (int b = 0; b < nb; b++) band_out[b] = ORC_VDIV((band_e[b] * (1.0f - wabs[b])) * geo, total * total, inv);
                     emit(env, id, i, 1, t, contrib, posx, posy, band_out, ctr);
                 }
             }
@@ -351,8 +383,9 @@ static void trace_one(const trace_env *env, uint32_t id, orc_counters *ctr) {
                     float jy = fmaf(rx, s, ry * c);
                     rx = jx; ry = jy;
                 }
-                float inv = 1.0f / sqrtf(dot2(rx, ry, rx, ry));
-                dirx = rx * inv; diry = ry * inv;
+                float len = sqrtf(dot2(rx, ry, rx, ry));
+                float inv = 1.0f / len;
+                dirx = ORC_VDIV(rx, len, inv); diry = ORC_VDIV(ry, len, inv);
                 speed = next_speed;
                 if (entering) wall_depth++; else wall_depth = wall_depth - 1 > 0 ? wall_depth - 1 : 0;
                 posx = fmaf(dirx, ORC_EPS, posx);
@@ -371,8 +404,9 @@ static void trace_one(const trace_env *env, uint32_t id, orc_counters *ctr) {
         float dfy = fmaf(nx, s, ny * c);
         float mx = fmaf(wall->scattering, dfx - spx, spx);
         float my = fmaf(wall->scattering, dfy - spy, spy);
-        float inv = 1.0f / sqrtf(dot2(mx, my, mx, my));
-        dirx = mx * inv; diry = my * inv;
+        float len = sqrtf(dot2(mx, my, mx, my));
+        float inv = 1.0f / len;
+        dirx = ORC_VDIV(mx, len, inv); diry = ORC_VDIV(my, len, inv);
         posx = fmaf(nx, ORC_EPS, posx);
         posy = fmaf(ny, ORC_EPS, posy);
     }

@@ -881,16 +881,23 @@ int rar_exchange_create(rar_context *ctx, int64_t capacity_words, void *handle_o
         X = Exchange();
         RAR_CUDA(ctx, e);
     }
-    // The handle names the allocation the driver carved the region from; ship the region's offset in it.
+    // The handle names the allocation the driver carved the region from; ship the region's offset in it.  Without the
+    // offset a peer would address the wrong bytes (silent corruption), so failing to learn it is an error.
     typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     unsigned long long base = 0;
     size_t span = 0;
-    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
-        ((range_fn)fn)(&base, &span, (unsigned long long)(uintptr_t)X.region) == 0 && base)
-        h.offset = (unsigned long long)(uintptr_t)X.region - base;
+    const bool have_range = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
+                            ((range_fn)fn)(&base, &span, (unsigned long long)(uintptr_t)X.region) == 0 && base;
     cudaGetLastError();
+    if (!have_range) {
+        cudaFree(X.region);
+        X = Exchange();
+        return fail(ctx, RAR_ERR_UNSUPPORTED, "cannot query the address range of the exchange region (cuMemGetAddressRange): "
+                                              "its offset inside the IPC allocation is unknown");
+    }
+    h.offset = (unsigned long long)(uintptr_t)X.region - base;
     h.cap_words = (unsigned long long)capacity_words;
     std::memcpy(handle_out, &h, sizeof h);
     return RAR_OK;
@@ -907,7 +914,14 @@ int rar_exchange_connect(rar_context *ctx, int32_t rank, int32_t world, const vo
     for (int r = 0; r < world; r++) {
         ExchangeHandle h;
         std::memcpy(&h, hs + r, sizeof h);
-        if ((long long)h.cap_words != X.cap_words) return fail(ctx, RAR_ERR_INVALID, "exchange capacity differs between ranks");
+        if ((long long)h.cap_words != X.cap_words) {
+            for (int k = 0; k < r; k++)  // leave nothing mapped behind a failed connect
+                if (X.opened[k]) {
+                    cudaIpcCloseMemHandle(X.opened[k]);
+                    X.opened[k] = nullptr;
+                }
+            return fail(ctx, RAR_ERR_INVALID, "exchange capacity differs between ranks");
+        }
         if (r == rank) {
             X.peer[r] = X.region;
             continue;
@@ -1297,6 +1311,8 @@ int rar_poll(rar_context *ctx, int32_t ticket) {
         return 0;
     }
     T->failed = true;
+    T->active = false;  // released: the mirrors drop a failed request without calling convolve_end (RayTraceManager.cs:119)
+    cudaGetLastError();
     return fail(ctx, RAR_ERR_CUDA, "ticket failed: %s", cudaGetErrorString(e));
 }
 

@@ -42,13 +42,24 @@ def allreduce_histogram(hist_tensor, group=None) -> None:
 
 
 class DeviceHistogram:
-    """Zero-copy torch view of a context's IR slot (rar_ir_device_ptr) for the collective."""
+    """Zero-copy torch view of a context's IR slot (rar_ir_device_ptr) for the collective.
+
+    The library treats a slot whose address has been handed out as externally writable from then on (its cached
+    spectra are never reused) and refuses to reallocate it; `check()` re-queries the address for callers that want
+    to assert the view is still the slot."""
 
     def __init__(self, ctx, slot: int, device):
         import torch
+        self._ctx, self._slot = ctx, slot
         ptr, n = ctx.ir_device_ptr(slot)
+        self._ptr, self._n = ptr, n
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         self.tensor = torch.as_tensor(self, device=device)
+
+    def check(self) -> None:
+        ptr, n = self._ctx.ir_device_ptr(self._slot)
+        if (ptr, n) != (self._ptr, self._n):
+            raise RuntimeError("the slot was reconfigured after its device address was taken: re-create the view")
 
 
 def gather_handles(handle: bytes, group=None):

@@ -144,9 +144,9 @@ def test_band_edge_errors(ctx):
         ctx.set_band_edges([100, 5000, 24000], 48000)              # does not start at 0
     ctx.set_band_edges([0, 1000, 24000], 48000)                    # two bands ...
     try:
-        ctx.ir_write(5, np.ones(3 * 100, np.float32) * 1e-3, bands=3)
+        ctx.ir_write(57, np.ones(3 * 100, np.float32) * 1e-3, bands=3)
         with pytest.raises(_capi.RarError) as e:                   # ... but the slot has three
-            ctx.synthesize_ir(5, 100)
+            ctx.synthesize_ir(57, 100)
         assert e.value.code == -3
     finally:
         ctx.set_band_edges(None, 48000)

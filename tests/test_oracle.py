@@ -245,3 +245,46 @@ def test_band_filter_bank_properties(oracle):
     up = np.zeros((bins * 4, bands), np.int64)
     up[::4] = hist.reshape(bins, bands)
     assert np.array_equal(s4, oracle.synthesize_ir(up.ravel(), bins * 4, bands, 1))
+
+
+# SURVEY.md Appendix B.2, every row: the four corners of each box in segment order (segment k runs corner k -> k+1)
+# and the four outward normals, rounded to 6 significant digits there.
+_B2 = {
+    "smoll": [
+        ([(-50, 9.5), (50, 9.5), (50, 10.5), (-50, 10.5)], [(0, -1), (1, 0), (0, 1), (-1, 0)]),
+        ([(-49.99, -5.5), (50.01, -5.5), (50.01, -4.5), (-49.99, -4.5)], [(0, -1), (1, 0), (0, 1), (-1, 0)]),
+        ([(-19.5, -10), (-19.5, 10), (-20.5, 10), (-20.5, -10)], [(1, 0), (0, 1), (-1, 0), (0, -1)]),
+        ([(20.5, -10), (20.5, 10), (19.5, 10), (19.5, -10)], [(1, 0), (0, 1), (-1, 0), (0, -1)]),
+        ([(-38.5389, -35.0726), (15.7785, 48.8894), (14.9389, 49.4326), (-39.3785, -34.5294)],
+         [(.83962, -.543175), (.543175, .83962), (-.83962, .543175), (-.543175, -.83962)]),
+    ],
+    "big": [
+        ([(-500, 99.5), (500, 99.5), (500, 100.5), (-500, 100.5)], [(0, -1), (1, 0), (0, 1), (-1, 0)]),
+        ([(-499.99, -50.5), (500.01, -50.5), (500.01, -49.5), (-499.99, -49.5)], [(0, -1), (1, 0), (0, 1), (-1, 0)]),
+        ([(-199.5, -100), (-199.5, 100), (-200.5, 100), (-200.5, -100)], [(1, 0), (0, 1), (-1, 0), (0, -1)]),
+        ([(200.5, -100), (200.5, 100), (199.5, 100), (199.5, -100)], [(1, 0), (0, 1), (-1, 0), (0, -1)]),
+        ([(-386.189, -350.726), (156.985, 488.894), (148.589, 494.326), (-394.585, -345.294)],
+         [(.83962, -.543175), (.543175, .83962), (-.83962, .543175), (-.543175, -.83962)]),
+    ],
+}
+
+
+@pytest.mark.parametrize("room", ["smoll", "big"])
+def test_every_segment_of_appendix_b2_to_six_significant_digits(room):
+    """All 20 segments of both bundled rooms -- start, end, normal and material -- against the table the survey derived
+    from the scene transforms (Helpers/SceneHelper.cs:49-58,78-97), to the six significant digits it prints."""
+    w = (scenes.smoll_room() if room == "smoll" else scenes.big_room()).walls
+
+    def six(a, b):        # equal after rounding to 6 significant digits (absolute 5e-7 near zero: sin/cos of 90 degrees)
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return np.all(np.abs(a - b) <= np.maximum(5.1e-6 * np.abs(b), 5e-7))
+    border, mat = (0.507, 0.5, 0.271, 0.01), (0.148, 1.0, 1.0, 0.6)
+    for box, (corners, normals) in enumerate(_B2[room]):
+        for k in range(4):
+            seg = w[4 * box + k]
+            assert six(seg["start"], corners[k]), (box, k, seg["start"], corners[k])
+            assert six(seg["end"], corners[(k + 1) % 4]), (box, k, seg["end"])
+            assert six(seg["normal"], normals[k]), (box, k, seg["normal"])
+            m = mat if box == 4 else border
+            assert (float(seg["absorption"]), float(seg["scattering"]), float(seg["transmission"]), float(seg["ior"])) == \
+                tuple(float(np.float32(v)) for v in m)

@@ -54,6 +54,8 @@ def launches(csv_path, title):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01_final"
+    if tag.startswith("-") or "/" in tag:      # `--help` once became a file-name prefix under profiles/
+        raise SystemExit(__doc__)
     jobs = [("prof_c2_final", "ncu_trace_c2", "trace_deposit_kernel on BASELINE config 2 (tools/run_trace.py c2)"),
             ("prof_maze_final", "ncu_trace_maze", "trace_deposit_kernel on the 10 000-wall maze, brute force (tools/run_trace.py maze)"),
             ("prof_grid_final", "ncu_trace_grid", "trace_deposit_kernel on the 10 000-wall maze, RAR_FLAG_USE_GRID (RAR_GRID=1 tools/run_trace.py maze)"),
