@@ -1092,8 +1092,12 @@ static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, i
     if (params->debug_ray_count > 0) {
         const int rows = params->debug_ray_count > 100 ? params->debug_ray_count : 100;
         const long long entries = (long long)rows * (params->max_bounce_count + 1);
+        // The kernel re-initialises the row of every ray it traces, so the usual whole-dispatch frame needs no separate
+        // clear of the buffer; a launch that does not cover all rows (a ray-range shard) clears it the old way.
+        if ((size_t)entries > ctx->d_debug.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // growth frees a buffer in use
         RAR_CUDA(ctx, ctx->d_debug.reserve((size_t)entries));
-        RAR_CUDA(ctx, cudaMemsetAsync(ctx->d_debug.p, 0, (size_t)entries * sizeof(f4), ctx->stream));
+        if (a.ray_begin > 0 || a.ray_end < rows)
+            RAR_CUDA(ctx, cudaMemsetAsync(ctx->d_debug.p, 0, (size_t)entries * sizeof(f4), ctx->stream));
         ctx->debug_entries = (int)entries;
         a.debug_rays = ctx->d_debug.p;
         a.debug_ray_count = params->debug_ray_count;

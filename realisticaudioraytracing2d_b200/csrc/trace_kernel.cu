@@ -403,7 +403,15 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
         if (a.debug_rays != nullptr && alive && frame == 0) {
             const long long row = (long long)id * (max_b + 1);
             dbg_flags = (id < 100u ? 1 : 0) | (id < (uint32_t)a.debug_ray_count ? 2 : 0);
-            if (row + max_b >= a.debug_capacity) dbg_flags = 0;
+            // every row of the buffer is re-initialised by the thread of that ray (rows exist for ids below
+            // max(100, debugRayCount)): vertices this frame does not reach read as zero, and no separate clear of the
+            // buffer is enqueued before the launch
+            if (row + max_b < a.debug_capacity) {
+                f4 *rowp = a.debug_rays + row;
+                for (int k = 0; k <= max_b; k++) rowp[k] = f4{0.f, 0.f, 0.f, 0.f};
+            } else {
+                dbg_flags = 0;
+            }
             if (dbg_flags) {
                 dbg = a.debug_rays + row;
                 if (dbg_flags & 1) dbg[0] = f4{r.px, r.py, r.energy, 0.0f};

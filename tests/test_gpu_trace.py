@@ -170,6 +170,27 @@ def test_debug_rays(ctx):
     assert np.all(rays[:, 1, 2] == np.float32(sc.input_gain))       # energy before the first absorption
 
 
+def test_debug_rays_hold_no_stale_vertices(ctx):
+    """The kernel re-initialises the debug row of every ray it traces (no separate clear per frame): the buffer after a
+    frame does not depend on the frames before it, and rows without a ray read as zero."""
+    sc = scenes.smoll_room()
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, sc.impulse_length, 1)
+    n4 = 100 * (sc.max_bounces + 1)
+
+    def frame(f, **over):
+        ctx.trace(capi_params(_capi, trace_kwargs(sc, debug_ray_count=100, rng_state_offset=f, **over)), 0)
+        return ctx.get_debug_rays(n4)
+    first = frame(5)
+    other = frame(6)
+    again = frame(5)
+    assert np.array_equal(first, again) and not np.array_equal(first, other)
+    few = frame(5, ray_count=64).reshape(100, sc.max_bounces + 1, 4)      # 64 rays, 100 rows: rows 64.. have no ray
+    assert few[:64].any() and not few[64:].any()
+    shard = frame(5, ray_begin=32, ray_end=64).reshape(100, sc.max_bounces + 1, 4)   # a shard clears the whole buffer first
+    assert shard[32:64].any() and not shard[:32].any() and not shard[64:].any()
+
+
 def test_full_size_shoebox_properties(ctx, oracle):
     """BASELINE config 2 at full size (1M rays x 32 bounces): size-independent checks.
     (a) linearity in input_gain by a power of two is exact in fixed point up to the truncation of each deposit;
