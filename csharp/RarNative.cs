@@ -57,6 +57,7 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_set_walls(IntPtr ctx, [In] Segment[] segments, int n);
         [DllImport(Lib)] public static extern int rar_set_wall_band_absorption(IntPtr ctx, [In] float[] absorption, int n, int bands);
 
+        [DllImport(Lib)] public static extern int rar_set_air_absorption(IntPtr ctx, [In] float[] alphaPerMetre, int bands);
         [DllImport(Lib)] public static extern int rar_ir_clear(IntPtr ctx, int slot, int impulseLength, int bands);
         [DllImport(Lib)] public static extern int rar_ir_read(IntPtr ctx, int slot, [Out] float[] dst, long n);
         [DllImport(Lib)] public static extern int rar_ir_read_fixed(IntPtr ctx, int slot, [Out] long[] dst, long n);

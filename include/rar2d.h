@@ -161,6 +161,15 @@ RAR_API int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t
  * equal the current wall count.  Slots of more than 8 bands are traced in chunks of 8 bands. */
 RAR_API int rar_set_wall_band_absorption(rar_context *ctx, const float *absorption, int32_t n, int32_t bands);
 
+/* Banded model, air absorption: band b of every arrival of a banded trace is additionally scaled by
+ * exp(-alpha_per_m[b] * d), d = the arrival's whole path length in metres (source -> walls -> listener).  The
+ * broadband energy -- and with it every threshold and branch of Raytrace2D.compute:66-155 -- is untouched, so ray
+ * paths do not change.  exp is a fixed polynomial kernel of the arithmetic contract (histograms stay bit-exact
+ * against the oracle).  `bands` must equal the band count of the traces that follow; NULL or bands == 0 switches the
+ * attenuation off (the default).  The reference has no air model: its placeholder is the `muffle` factor of
+ * RaytraceOcclusion2D.compute:125-126,247-248. */
+RAR_API int rar_set_air_absorption(rar_context *ctx, const float *alpha_per_m, int32_t bands);
+
 /* ---- impulse-response slots ------------------------------------------------------------------ */
 
 /* RayTraceManager.cs:169-177 ResetIR -> ClearImpulse (Raytrace2D.compute:167-172), plus the buffer

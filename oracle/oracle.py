@@ -82,6 +82,11 @@ def lib() -> C.CDLL:
         L.orc_trace.restype = C.c_int
         L.orc_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(TraceParams), C.c_void_p, C.c_void_p,
                                 i64, C.POINTER(i64), C.POINTER(Counters), C.c_int]
+        L.orc_trace_air.restype = C.c_int
+        L.orc_trace_air.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(TraceParams), C.c_void_p, C.c_void_p,
+                                    i64, C.POINTER(i64), C.POINTER(Counters), C.c_int]
+        L.orc_exp_neg.restype = f32
+        L.orc_exp_neg.argtypes = [f32, f32]
         L.orc_ir_to_float.restype = None
         L.orc_ir_to_float.argtypes = [C.c_void_p, i64, C.c_void_p]
         L.orc_convolve.restype = None
@@ -144,7 +149,8 @@ class TraceResult:
 
 
 def trace(walls: np.ndarray, params: TraceParams, band_abs: np.ndarray | None = None, hist: np.ndarray | None = None,
-          want_hist: bool = True, want_hits: bool = False, hit_cap: int | None = None, n_threads: int = 0) -> TraceResult:
+          want_hist: bool = True, want_hits: bool = False, hit_cap: int | None = None, n_threads: int = 0,
+          air: np.ndarray | None = None) -> TraceResult:
     walls = np.ascontiguousarray(walls, dtype=SEGMENT_DTYPE)
     bands = max(1, params.bands)
     if want_hist and hist is None:
@@ -160,7 +166,11 @@ def trace(walls: np.ndarray, params: TraceParams, band_abs: np.ndarray | None = 
         hits = np.zeros(hit_cap, dtype=HIT_DTYPE)
     cnt = C.c_int64(0)
     ctr = Counters()
-    rc = lib().orc_trace(walls.ctypes.data, len(walls), band_abs.ctypes.data if band_abs is not None else None,
+    if air is not None:
+        air = np.ascontiguousarray(air, dtype=np.float32)
+        assert air.shape == (bands,)
+    rc = lib().orc_trace_air(walls.ctypes.data, len(walls), band_abs.ctypes.data if band_abs is not None else None,
+                         air.ctypes.data if air is not None else None,
                          C.byref(params), hist.ctypes.data if want_hist else None,
                          hits.ctypes.data if hits is not None else None, hit_cap or 0, C.byref(cnt), C.byref(ctr),
                          n_threads)

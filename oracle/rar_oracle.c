@@ -221,6 +221,31 @@ ORC_API float orc_asinf(float x) {
     return (x < 0.0f) ? -r : r;
 }
 
+/* exp(-alpha * d), alpha >= 0 in 1/m, d a path length in m: the air attenuation of the banded model (this build's
+ * extension; the reference's placeholder is `muffle`, RaytraceOcclusion2D.compute:125-126,247-248).  Fixed kernel:
+ * y = (alpha*d) * (-log2 e); k = round(y) by the 1.5*2^23 trick; 2^(y-k) by a degree-6 polynomial; times 2^k. */
+ORC_API float orc_exp_neg(float alpha, float d) {
+#ifdef ORC_VARIANT_NAIVE
+    return expf(-(alpha * d));
+#endif
+    float y = (alpha * d) * -1.4426950408889634f;
+    if (!(y > -126.0f)) return 0.0f;
+    if (!(y < 0.0f)) return 1.0f;
+    const float MAGIC = 12582912.0f;
+    float kf = (y + MAGIC) - MAGIC;
+    float f = y - kf;
+    float p = fmaf(f, 1.5403530e-4f, 1.3333558e-3f);
+    p = fmaf(f, p, 9.6181291e-3f);
+    p = fmaf(f, p, 5.5504109e-2f);
+    p = fmaf(f, p, 2.4022651e-1f);
+    p = fmaf(f, p, 6.9314718e-1f);
+    p = fmaf(f, p, 1.0f);
+    uint32_t bits = (uint32_t)((int)kf + 127) << 23;
+    float scale;
+    memcpy(&scale, &bits, sizeof scale);
+    return p * scale;
+}
+
 /* ---- deposit (Raytrace2D.compute:157-165 ProcessHits, fixed-point instead of the racy float +=) ------- */
 
 ORC_API int64_t orc_quantize(float e) {
@@ -244,6 +269,7 @@ typedef struct {
     const orc_segment *walls;
     int n_walls;
     const float *band_abs; /* [n_walls][bands] or NULL */
+    const float *air;      /* [bands] air absorption in 1/m, or NULL */
     const orc_trace_params *p;
     int64_t *hist;         /* [impulse_length][bands], accumulated atomically */
     orc_hit *hits;
@@ -324,7 +350,10 @@ static void trace_one(const trace_env *env, uint32_t id, orc_counters *ctr) {
                 float total = dist + dl;
                 float denom = fmaxf(1.0f, total * total);
                 float e = energy / denom;
-                for (int b = 0; b < nb; b++) band_out[b] = band_e[b] / denom;
+                for (int b = 0; b < nb; b++) {
+                    band_out[b] = band_e[b] / denom;
+                    if (env->air) band_out[b] *= orc_exp_neg(env->air[b], total);
+                }
                 emit(env, id, i, 0, t, e, hx, hy, band_out, ctr);
             }
         }
@@ -354,7 +383,10 @@ static void trace_one(const trace_env *env, uint32_t id, orc_counters *ctr) {
                 float contrib = ORC_VDIV((energy * keep) * geo, total * total, inv);
                 if (contrib > 1e-5f) {
                     float t = time + dl / p->speed_of_sound;
-                    for (int b = 0; b < nb; b++) band_out[b] = ORC_VDIV((band_e[b] * (1.0f - wabs[b])) * geo, total * total, inv);
+                    for (int b = 0; b < nb; b++) {
+                        band_out[b] = ORC_VDIV((band_e[b] * (1.0f - wabs[b])) * geo, total * total, inv);
+                        if (env->air) band_out[b] *= orc_exp_neg(env->air[b], total);
+                    }
                     emit(env, id, i, 1, t, contrib, posx, posy, band_out, ctr);
                 }
             }
@@ -419,15 +451,24 @@ ORC_API int64_t orc_dispatch_threads(const orc_trace_params *p) {
     return ((int64_t)p->ray_count + 63) / 64 * 64;
 }
 
+ORC_API int orc_trace_air(const orc_segment *walls, int n_walls, const float *band_abs, const float *air, const orc_trace_params *p,
+                          int64_t *hist, orc_hit *hits, int64_t hit_cap, int64_t *hit_count, orc_counters *out_ctr, int n_threads);
+
 ORC_API int orc_trace(const orc_segment *walls, int n_walls, const float *band_abs, const orc_trace_params *p,
                       int64_t *hist, orc_hit *hits, int64_t hit_cap, int64_t *hit_count, orc_counters *out_ctr,
                       int n_threads) {
+    return orc_trace_air(walls, n_walls, band_abs, NULL, p, hist, hits, hit_cap, hit_count, out_ctr, n_threads);
+}
+
+/* The same with per-band air absorption (air: [bands] in 1/m, or NULL). */
+ORC_API int orc_trace_air(const orc_segment *walls, int n_walls, const float *band_abs, const float *air, const orc_trace_params *p,
+                          int64_t *hist, orc_hit *hits, int64_t hit_cap, int64_t *hit_count, orc_counters *out_ctr, int n_threads) {
     if (p->bands > ORC_MAX_BANDS) return -1;
     if (p->bands > 1 && !band_abs) return -2;
     int64_t lo = p->ray_begin, hi = p->ray_end;
     if (lo == 0 && hi == 0) hi = orc_dispatch_threads(p);
     int64_t hc = 0;
-    trace_env env = {walls, n_walls, band_abs, p, hist, hits, hit_cap, &hc};
+    trace_env env = {walls, n_walls, band_abs, p->bands > 1 ? air : NULL, p, hist, hits, hit_cap, &hc};
     orc_counters total;
     memset(&total, 0, sizeof total);
 #ifdef _OPENMP

@@ -63,6 +63,7 @@ SYMBOLS = {
     "rar_sync": (C.c_int, [_p]),
     "rar_set_walls": (C.c_int, [_p, _p, _i32]),
     "rar_set_wall_band_absorption": (C.c_int, [_p, _p, _i32, _i32]),
+    "rar_set_air_absorption": (C.c_int, [_p, _p, _i32]),
     "rar_ir_clear": (C.c_int, [_p, _i32, _i32, _i32]),
     "rar_ir_read": (C.c_int, [_p, _i32, _p, _i64]),
     "rar_ir_read_begin": (C.c_int, [_p, _i32, _i64, C.POINTER(_i32)]),
@@ -219,6 +220,14 @@ class Context:
     def set_wall_band_absorption(self, table: np.ndarray) -> None:
         t = np.ascontiguousarray(table, dtype=np.float32)
         self._ck(self._lib.rar_set_wall_band_absorption(self._h, t.ctypes.data if t.size else None, t.shape[0], t.shape[1]))
+
+    def set_air_absorption(self, alpha_per_m) -> None:
+        """rar_set_air_absorption: per-band air absorption in 1/m; None switches it off."""
+        if alpha_per_m is None:
+            self._ck(self._lib.rar_set_air_absorption(self._h, None, 0))
+            return
+        a = np.ascontiguousarray(alpha_per_m, dtype=np.float32)
+        self._ck(self._lib.rar_set_air_absorption(self._h, a.ctypes.data, len(a)))
 
     # IR slots ---------------------------------------------------------------------------------
     def ir_clear(self, slot: int, impulse_length: int, bands: int = 1) -> None:

@@ -128,6 +128,7 @@ struct rar_context {
     DevBuf<float> d_band_abs;
     int n_walls = -1;  // -1: never set
     int band_rows = 0, band_count = 0;
+    std::vector<float> air;  // air absorption per band, 1/m (empty: none); rar_set_air_absorption
     DevBuf<f2> d_end;                  // wall end points (the grid builder needs them unrounded)
     PinnedBuf<f4> h_planes;            // pinned staging of the geo | mat0 | mat1 | end planes of one upload
     cudaEvent_t walls_uploaded = nullptr;  // the staging buffer may be rewritten once this has completed
@@ -655,6 +656,19 @@ int rar_synthesize_ir(rar_context *ctx, int32_t slot, float *out, int64_t n) {
     return RAR_OK;
 }
 
+int rar_set_air_absorption(rar_context *ctx, const float *alpha_per_m, int32_t bands) {
+    RAR_ENTER(ctx);
+    if (!alpha_per_m || bands == 0) {
+        ctx->air.clear();
+        return RAR_OK;
+    }
+    if (bands < 2 || bands > 128) return fail(ctx, RAR_ERR_UNSUPPORTED, "bands must be 2..128");
+    for (int b = 0; b < bands; b++)
+        if (!(alpha_per_m[b] >= 0.0f && alpha_per_m[b] <= 1e6f)) return fail(ctx, RAR_ERR_INVALID, "air absorption must be finite and >= 0");
+    ctx->air.assign(alpha_per_m, alpha_per_m + bands);
+    return RAR_OK;
+}
+
 // ---- IR slots ---------------------------------------------------------------------------------------
 
 int rar_ir_clear(rar_context *ctx, int32_t slot, int32_t impulse_length, int32_t bands) {
@@ -1103,11 +1117,15 @@ static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, i
         a.debug_ray_count = params->debug_ray_count;
         a.debug_capacity = (int)entries;
     }
+    if (params->bands > 1 && !ctx->air.empty() && (int)ctx->air.size() != params->bands)
+        return fail(ctx, RAR_ERR_STATE, "rar_set_air_absorption was called for a different band count than this trace has");
     // A ray's path depends on the broadband material only, so a slot of more than 8 bands is filled by tracing the
     // same rays once per chunk of 8 bands (tests are counted for the first chunk only).
     for (int b0 = 0; b0 < params->bands; b0 += 8) {
         a.band_offset = b0;
         a.band_valid = params->bands - b0 < 8 ? params->bands - b0 : 8;
+        a.p.air_on = (params->bands > 1 && !ctx->air.empty()) ? 1 : 0;
+        for (int k = 0; k < 8; k++) a.p.air[k] = (a.p.air_on && b0 + k < params->bands) ? ctx->air[b0 + k] : 0.0f;
         if (b0 > 0) {
             a.counters = nullptr;
             a.debug_rays = nullptr;

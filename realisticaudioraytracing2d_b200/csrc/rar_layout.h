@@ -75,6 +75,8 @@ inline RayConsts ray_consts(const rar_trace_params &p) {
     c.count_executed = (p.flags & RAR_FLAG_COUNT_EXECUTED) ? 1 : 0;
     c.sample_rate_f = (float)p.sample_rate;
     c.impulse_length_f = (float)p.impulse_length;
+    c.air_on = 0;
+    for (int b = 0; b < 8; b++) c.air[b] = 0.0f;
     return c;
 }
 

@@ -44,6 +44,10 @@ struct RayConsts {
     float time_divisor;
     int count_executed;  // with COUNT: resolve (and count) only the shadow rays the production kernel resolves
     float sample_rate_f, impulse_length_f;  // (float) of the two integers above, converted once on the host
+    // banded model: air absorption of the (up to 8) bands this launch carries, 1/m; band arrivals are scaled by
+    // exp(-air[b] * path length) when air_on (rar_set_air_absorption)
+    int air_on;
+    float air[8];
 };
 
 // SPEC kernels (see Scene::kSpec): the refined reciprocal of the launch-invariant speed of sound, formed once per
@@ -458,7 +462,7 @@ struct BounceCtx {
     f4 m0;              // nx, ny, absorption, scattering
     f2 m1;              // transmission, ior
     float keep, dir_dot_n;
-    float nee_t, nee_e, geo, inv;
+    float nee_t, nee_e, geo, inv, total;  // total: path length source -> hit point -> listener of the estimate
     float band_keep[BANDS > 1 ? BANDS : 1];
 };
 
@@ -496,7 +500,10 @@ RAR_HD void listener_direct(const RayConsts &p, float lx, float ly, const RaySta
         direct.e = rar_div(r.energy, denom);
         if (BANDS > 1) {
 #pragma unroll
-            for (int b = 0; b < BANDS; b++) direct.band_e[b] = rar_div(r.band_e[b], denom);
+            for (int b = 0; b < BANDS; b++) {
+                direct.band_e[b] = rar_div(r.band_e[b], denom);
+                if (p.air_on) direct.band_e[b] *= exp_neg_poly(p.air[b], total);
+            }
         }
         if (COUNT) ctr->direct_hits += 1;
     }
@@ -567,6 +574,7 @@ RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<
         const float inv_dl = rcp_inrange(dl);
         const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
         const float total = r.dist + dl;
+        c.total = total;
         c.geo = cos_t * 0.5f;
         c.inv = rcp_inrange(total * total);
         c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
@@ -587,6 +595,7 @@ RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<
     const float inv_dl = rar_rcp(dl);  // toList / distList := toList * (1 / distList)
     const float cos_t = fmaxf(0.0f, dot2(enx, eny, tlx * inv_dl, tly * inv_dl));
     const float total = r.dist + dl;
+    c.total = total;
     c.geo = cos_t * 0.5f;
     c.inv = rar_rcp(total * total);
     c.nee_e = ((r.energy * c.keep) * c.geo) * c.inv;
@@ -601,7 +610,7 @@ RAR_HD void listener_nee(const RayConsts &p, float lx, float ly, const RayState<
 // :113-118: the estimate arrives iff it cleared the threshold and the listener is visible.
 template <int BANDS, bool COUNT>
 RAR_HD void nee_arrival(const RayState<BANDS> &r, const BounceCtx<BANDS> &c, bool visible, Arrival<BANDS> &nee,
-                        RayCounters *ctr) {
+                        RayCounters *ctr, const RayConsts *p = nullptr) {
     nee.has = 0;
     if (c.nee_candidate && visible) {
         nee.has = 1;
@@ -611,7 +620,10 @@ RAR_HD void nee_arrival(const RayState<BANDS> &r, const BounceCtx<BANDS> &c, boo
         nee.e = c.nee_e;
         if (BANDS > 1) {
 #pragma unroll
-            for (int b = 0; b < BANDS; b++) nee.band_e[b] = ((r.band_e[b] * c.band_keep[b]) * c.geo) * c.inv;
+            for (int b = 0; b < BANDS; b++) {
+                nee.band_e[b] = ((r.band_e[b] * c.band_keep[b]) * c.geo) * c.inv;
+                if (p && p->air_on) nee.band_e[b] *= exp_neg_poly(p->air[b], c.total);
+            }
         }
         if (COUNT) ctr->nee_hits += 1;
     }
@@ -718,7 +730,7 @@ template <int BANDS, bool COUNT, bool OPAQUE = false, class Scene>
 RAR_HD bool bounce_finish(const Scene &sc, const RayConsts &p, RayState<BANDS> &r, Arrival<BANDS> &nee,
                           const BounceCtx<BANDS> &c, bool visible, RayCounters *ctr) {
     (void)sc;
-    nee_arrival<BANDS, COUNT>(r, c, visible, nee, ctr);
+    nee_arrival<BANDS, COUNT>(r, c, visible, nee, ctr, &p);
     return bounce_scatter<BANDS, OPAQUE, Scene::kSpec>(p, r, c);
 }
 

@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_cons
                 }
                 Arrival<BANDS> nee;
                 nee.has = 0;
-                if (hit_wall) nee_arrival<BANDS, COUNT>(r, c, visible, nee, &ctr);
+                if (hit_wall) nee_arrival<BANDS, COUNT>(r, c, visible, nee, &ctr, &a.p);
                 __syncwarp();
                 deposit_hist<BANDS, true>(a, a.listener_hists[l], nee, lane);
             }

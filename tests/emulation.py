@@ -36,7 +36,7 @@ def lib():
     return _lib
 
 
-def trace(O, walls, params, band_abs=None, counting=True):
+def trace(O, walls, params, band_abs=None, counting=True, air=None):
     """Runs the product's ray logic on the host. `params` is an oracle TraceParams (same layout as
     rar_trace_params).  Returns (hist, hits sorted by ray/bounce/kind, counters dict)."""
     L = lib()
@@ -49,11 +49,14 @@ def trace(O, walls, params, band_abs=None, counting=True):
     ctr = O.Counters()
     walls = np.ascontiguousarray(walls)
     ba = np.ascontiguousarray(band_abs, dtype=np.float32) if band_abs is not None else None
+    a = np.ascontiguousarray(air, dtype=np.float32) if air is not None else None
+    L.emu_set_air(C.c_void_p(a.ctypes.data) if a is not None else None, len(a) if a is not None else 0)
     fn = L.emu_trace if counting else L.emu_trace_nocount
     fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                    C.POINTER(C.c_int64), C.POINTER(O.Counters)]
     rc = fn(walls.ctypes.data if len(walls) else None, len(walls), ba.ctypes.data if ba is not None else None,
                      C.addressof(params), hist.ctypes.data, hits.ctypes.data, cap, C.byref(cnt), C.byref(ctr))
+    L.emu_set_air(None, 0)
     assert rc == 0, rc
     hits = hits[: cnt.value]
     hits = hits[np.lexsort((hits["kind"], hits["bounce"], hits["ray"]))]

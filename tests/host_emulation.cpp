@@ -32,10 +32,16 @@ using HostScene = HostSceneT<false>;
 
 struct Hit { float t, e, x, y; uint32_t ray; uint16_t bounce, kind; };
 
+std::vector<float> g_air;  // per-band air absorption for the next emu_trace calls (empty: none)
+
 template <int BANDS, bool COUNT, bool OPAQUE, class SceneT>
 void run(const SceneT &sc, const rar_trace_params &p, long long *hist, Hit *hits, long long cap, long long *count,
          rar::RayCounters &ctr) {
     rar::RayConsts c = rar::ray_consts(p);
+    if (BANDS > 1 && (int)g_air.size() == BANDS) {
+        c.air_on = 1;
+        for (int b = 0; b < BANDS; b++) c.air[b] = g_air[b];
+    }
     const rar::SpecConsts spc = rar::spec_consts(c);
     long long lo, hi;
     rar::ray_range(p, lo, hi);
@@ -124,6 +130,9 @@ static int emu_trace_impl(bool counting, const rar_segment *walls, int n, const 
     }
     return 0;
 }
+
+extern "C" __attribute__((visibility("default")))
+void emu_set_air(const float *alpha, int n) { g_air.assign(alpha, alpha + (alpha ? n : 0)); }
 
 // counting != 0: the instantiation that keeps the reference's test counters (always resolves the shadow ray);
 // counting == 0: the production instantiation (skips shadow rays whose estimate cannot clear the threshold).

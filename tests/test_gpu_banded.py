@@ -137,6 +137,48 @@ def test_batched_responses_from_slots(ctx, oracle):
             cv.destroy()
 
 
+@pytest.mark.parametrize("case", ["maze300_b8", "maze10000_b8", "shoebox_b8", "maze_b20", "grid"])
+def test_air_absorption_bit_exact(ctx, oracle, case):
+    """rar_set_air_absorption: every band arrival scaled by exp(-alpha_b * path length), a fixed polynomial kernel of
+    the arithmetic contract: histograms bit-exact against the oracle in the per-thread, cooperative, four-wall
+    (range-checked-once), chunked (20 bands) and grid kernels; switching it off restores the plain banded trace."""
+    bands, flags = 8, 0
+    if case == "maze300_b8":
+        sc = scenes.maze(n_segments=300, ray_count=20_000, max_bounces=12, bands=8, seed=5)
+    elif case == "maze10000_b8":
+        sc = scenes.maze(n_segments=10000, ray_count=20_000, max_bounces=16, bands=8)
+    elif case == "shoebox_b8":
+        sc = scenes.shoebox(ray_count=50_000, max_bounces=24, scattering=0.2)
+        sc.band_absorption = np.random.default_rng(5).uniform(0.02, 0.3, size=(4, 8)).astype(np.float32)
+    elif case == "maze_b20":
+        sc, bands = scenes.maze(n_segments=600, ray_count=10_000, max_bounces=10, bands=20, seed=3), 20
+    else:
+        sc, flags = scenes.maze(n_segments=2000, ray_count=20_000, max_bounces=12, bands=8, seed=2), _capi.RAR_FLAG_USE_GRID
+    air = np.geomspace(1e-4, 0.08, bands).astype(np.float32)
+    air[0] = 0.0
+    kw = trace_kwargs(sc, bands=bands, impulse_length=24000, flags=flags)
+    n = 24000 * bands
+    ctx.set_walls(sc.walls)
+    ctx.set_wall_band_absorption(sc.band_absorption)
+    O = oracle
+    try:
+        ctx.set_air_absorption(air)
+        ctx.ir_clear(6, 24000, bands)
+        ctx.trace(capi_params(_capi, kw), 6)
+        want = O.trace(oracle_walls(O, sc.walls), oracle_params(O, dict(kw, flags=0)), band_abs=sc.band_absorption, air=air).hist
+        assert np.array_equal(ctx.ir_read_fixed(6, n), want) and np.count_nonzero(want) > 1000
+        with pytest.raises(_capi.RarError):                       # the table is for `bands` bands
+            ctx.set_air_absorption(air[:-1])
+            ctx.ir_clear(7, 24000, bands)
+            ctx.trace(capi_params(_capi, kw), 7)
+    finally:
+        ctx.set_air_absorption(None)
+    ctx.ir_clear(6, 24000, bands)
+    ctx.trace(capi_params(_capi, kw), 6)
+    plain = O.trace(oracle_walls(O, sc.walls), oracle_params(O, dict(kw, flags=0)), band_abs=sc.band_absorption).hist
+    assert np.array_equal(ctx.ir_read_fixed(6, n), plain) and not np.array_equal(plain, want)
+
+
 def test_band_edge_errors(ctx):
     with pytest.raises(_capi.RarError):
         ctx.set_band_edges([0, 5000, 4000, 24000], 48000)          # not ascending

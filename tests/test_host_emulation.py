@@ -187,3 +187,15 @@ def test_grid_mode_random_soup_of_segments(oracle):
     sc.walls, sc.source, sc.listener = walls, (25.0, 25.0), (30.0, 22.0)
     r = _check_grid(oracle, sc, trace_kwargs(sc, ray_count=4000, max_bounce_count=12))
     assert r.counters["ray_bounces"] > 20000
+
+
+def test_air_attenuation_host_logic_matches_the_oracle(oracle):
+    """rar_ray.cuh's band arrivals with air absorption (counting and production instantiations) against the oracle."""
+    sc = scenes.maze(n_segments=300, ray_count=6000, max_bounces=12, bands=8, seed=5)
+    air = np.array([0.0, 1e-4, 5e-4, 1e-3, 3e-3, 1e-2, 3e-2, 0.1], np.float32)
+    P = oracle_params(oracle, trace_kwargs(sc, bands=8, impulse_length=12000))
+    want = oracle.trace(oracle_walls(oracle, sc.walls), P, band_abs=sc.band_absorption, air=air).hist
+    assert np.count_nonzero(want) > 3000
+    for counting in (True, False):
+        got, _, _ = emulation.trace(oracle, oracle_walls(oracle, sc.walls), P, band_abs=sc.band_absorption, counting=counting, air=air)
+        assert np.array_equal(got, want), counting

@@ -288,3 +288,26 @@ def test_every_segment_of_appendix_b2_to_six_significant_digits(room):
             m = mat if box == 4 else border
             assert (float(seg["absorption"]), float(seg["scattering"]), float(seg["transmission"]), float(seg["ior"])) == \
                 tuple(float(np.float32(v)) for v in m)
+
+
+def test_air_attenuation_kernel_and_trace(oracle):
+    """The banded model's air absorption (this build's extension): exp(-alpha d) as a fixed polynomial kernel --
+    accurate to 4e-6 relative down to the smallest normal number, exactly 0 below and exactly 1 at d = 0 -- scales the
+    BAND energies of every arrival and nothing else (band with alpha = 0, counters and ray paths unchanged)."""
+    xs = np.concatenate([np.linspace(0, 87, 5001), [0.0, 1e-8, 87.3]]).astype(np.float32)
+    got = np.array([oracle.lib().orc_exp_neg(1.0, float(x)) for x in xs])
+    want = np.exp(-xs.astype(np.float64))
+    assert np.max(np.abs(got - want) / want) < 4e-6
+    assert oracle.lib().orc_exp_neg(0.5, 0.0) == 1.0 and oracle.lib().orc_exp_neg(1.0, 200.0) == 0.0
+    assert oracle.lib().orc_exp_neg(2.0, 3.0) == oracle.lib().orc_exp_neg(3.0, 2.0)
+    sc = scenes.maze(n_segments=300, ray_count=8000, max_bounces=12, bands=8, seed=5)
+    air = np.array([0.0, 1e-4, 5e-4, 1e-3, 3e-3, 1e-2, 3e-2, 0.1], np.float32)
+    P = oracle_params(oracle, trace_kwargs(sc, bands=8, impulse_length=12000))
+    r0 = oracle.trace(oracle_walls(oracle, sc.walls), P, band_abs=sc.band_absorption)
+    r1 = oracle.trace(oracle_walls(oracle, sc.walls), P, band_abs=sc.band_absorption, air=air)
+    h0, h1 = r0.hist.reshape(-1, 8), r1.hist.reshape(-1, 8)
+    assert r0.counters == r1.counters and np.count_nonzero(h0) > 5000
+    assert np.array_equal(h0[:, 0], h1[:, 0])                                  # alpha = 0
+    ratio = h1.sum(0) / h0.sum(0)
+    assert np.all(np.diff(ratio) < 0) and ratio[-1] < 0.1 < ratio[4]            # more absorption, less energy
+    assert np.all(h1 <= h0)
