@@ -65,25 +65,33 @@ def test_frame_rate_entry_points_return_while_the_device_is_busy(ctx, oracle):
     ctx.ir_clear(31, n, 8)
     ctx.trace_listeners(capi_params(_capi, trace_kwargs(small)), listeners, 40)
     ctx.trace(capi_params(_capi, trace_kwargs(small, flags=_capi.RAR_FLAG_USE_GRID)), 40)
+    ctx.trace(capi_params(_capi, trace_kwargs(small, bands=8)), 31)   # (a kernel's very first launch loads its code, which waits for the device)
     cv.set_irs(0, irs)
     ctx.sync()
     try:
-        ticket, _ = _busy(ctx)
-        t0 = time.perf_counter()
-        ctx.set_walls(small.walls)                                        # UpdateGeometry (RayTraceManager.cs:246-250)
-        ctx.set_wall_band_absorption(small.band_absorption)
+        ticket, _ = _busy(ctx, 0.6)
+        spent = {}
+
+        def timed(name, fn, *a):
+            t = time.perf_counter()
+            fn(*a)
+            spent[name] = spent.get(name, 0.0) + (time.perf_counter() - t) * 1e3
+
+        timed("set_walls", ctx.set_walls, small.walls)                   # UpdateGeometry (RayTraceManager.cs:246-250)
+        timed("set_wall_band_absorption", ctx.set_wall_band_absorption, small.band_absorption)
         for l in range(16):
-            ctx.ir_clear(40 + l, n, 1)
-        ctx.ir_clear(31, n, 8)
-        ctx.trace(capi_params(_capi, trace_kwargs(small, flags=_capi.RAR_FLAG_USE_GRID)), 40)   # builds the grid on the device
-        ctx.trace(capi_params(_capi, trace_kwargs(small, bands=8)), 31)
-        ctx.trace_listeners(capi_params(_capi, trace_kwargs(small)), listeners, 40)
-        cv.set_irs(0, irs)
-        dt = time.perf_counter() - t0
+            timed("ir_clear", ctx.ir_clear, 40 + l, n, 1)
+        timed("ir_clear", ctx.ir_clear, 31, n, 8)
+        timed("trace (grid built on the device)", ctx.trace, capi_params(_capi, trace_kwargs(small, flags=_capi.RAR_FLAG_USE_GRID)), 40)
+        timed("trace (8 bands)", ctx.trace, capi_params(_capi, trace_kwargs(small, bands=8)), 31)
+        timed("trace_listeners", ctx.trace_listeners, capi_params(_capi, trace_kwargs(small)), listeners, 40)
+        timed("conv.set_irs", cv.set_irs, 0, irs)
+        dt = sum(spent.values()) * 1e-3
         still_running = not ctx.poll(ticket)
         ctx.ir_read_end(ticket, 16)
-        assert still_running, "the long kernel finished before the calls returned: nothing was demonstrated"
-        assert dt < 0.05, f"the calls took {dt * 1e3:.1f} ms of host time behind a busy device"
+        report = ", ".join(f"{k} {v:.2f} ms" for k, v in spent.items())
+        assert dt < 0.05, f"the calls took {dt * 1e3:.1f} ms of host time behind a busy device: {report}"
+        assert still_running, f"the long kernel finished before the calls returned ({report}): nothing was demonstrated"
         # ... and what they enqueued is right
         want = oracle.trace(oracle_walls(oracle, small.walls), oracle_params(oracle, dict(trace_kwargs(small), listener=(float(listeners[3, 0]), float(listeners[3, 1]))))).hist
         assert np.array_equal(ctx.ir_read_fixed(43, n), want)

@@ -1,6 +1,7 @@
 """Single-process multi-GPU path (what a one-process host such as Unity uses): one context per device, disjoint ray
-ranges, rar_allreduce_slots over NVLink peer memory.  Needs >= 2 GPUs (skipped on a 1-GPU box; run with
-`gpurun --gpus 2`)."""
+ranges, rar_allreduce_slots over NVLink peer memory.  On a 1-GPU box the same code runs with two contexts on the one
+device (the reduce kernel then reads its peer's histogram from local memory), so the sharding logic and the kernel are
+exercised there too; `gpurun --gpus 2` and up give the real peer-memory path."""
 import numpy as np
 import pytest
 
@@ -24,14 +25,12 @@ def test_single_context_allreduce_is_a_noop(ctx):
 
 @pytest.mark.parametrize("bands", [1, 8])
 def test_peer_memory_allreduce_matches_unsharded_trace(oracle, bands):
-    n_dev = _device_count()
-    if n_dev < 2:
-        pytest.skip("needs at least 2 GPUs")
-    n_dev = min(n_dev, 8)
+    real = _device_count()
+    n_dev = min(max(real, 2), 8)                      # at least two contexts, wrapped onto the devices there are
     sc = scenes.maze(n_segments=600, ray_count=40_000, max_bounces=10, bands=8)
     kw = trace_kwargs(sc, bands=bands)
     n = kw["impulse_length"]
-    ctxs = [_capi.Context(d) for d in range(n_dev)]
+    ctxs = [_capi.Context(d % real) for d in range(n_dev)]
     try:
         total = dispatched_threads(kw["ray_count"])
         for r, c in enumerate(ctxs):
