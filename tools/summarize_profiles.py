@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns the ncu artefacts in gpurun_out/ into the text summaries committed under profiles/.
 
-    python tools/summarize_profiles.py <tag>      # e.g. r01_final
+    python tools/summarize_profiles.py <tag>      # r02 (default) or r01_final
 """
 import collections
 import csv
@@ -52,15 +52,25 @@ def launches(csv_path, title):
     return "\n".join(out)
 
 
+JOBS = {
+    "r01_final": [("prof_c2_final", "ncu_trace_c2", "trace_deposit_kernel on BASELINE config 2 (tools/run_trace.py c2)"),
+                  ("prof_maze_final", "ncu_trace_maze", "trace_deposit_kernel on the 10 000-wall maze, brute force (tools/run_trace.py maze)"),
+                  ("prof_grid_final", "ncu_trace_grid", "trace_deposit_kernel on the 10 000-wall maze, RAR_FLAG_USE_GRID (RAR_GRID=1 tools/run_trace.py maze)"),
+                  ("prof_cmac_final", "ncu_cmac", "stream_cmac_kernel on BASELINE config 5 (tools/run_trace.py conv)")],
+    # tools/profile_round2.sh
+    "r02": [("r02_c2", "ncu_trace_c2", "trace_deposit_kernel<..., FAST=3> on BASELINE config 2 (tools/run_trace.py c2): four-wall, range-checked-once variant"),
+            ("r02_c2_guarded", "ncu_trace_c2_guarded", "the same dispatch with RAR_NO_FAST=1: the kernel with a guard around every division / square root"),
+            ("r02_maze8", "ncu_trace_maze8", "trace_deposit_kernel on the 10 000-wall maze, 8 bands, brute force (tools/run_trace.py maze8)"),
+            ("r02_c1", "ncu_trace_c1", "trace_deposit_kernel on BASELINE config 1, one 15 000-ray frame of SmollRoom (tools/run_trace.py c1)"),
+            ("r02_band_synth", "ncu_band_synth", "band_synth_kernel: 16 banded slots x 480 000 bins x 8 bands in one launch (tools/run_bench_leg.py banded)")],
+}
+
+
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01_final"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     if tag.startswith("-") or "/" in tag:      # `--help` once became a file-name prefix under profiles/
         raise SystemExit(__doc__)
-    jobs = [("prof_c2_final", "ncu_trace_c2", "trace_deposit_kernel on BASELINE config 2 (tools/run_trace.py c2)"),
-            ("prof_maze_final", "ncu_trace_maze", "trace_deposit_kernel on the 10 000-wall maze, brute force (tools/run_trace.py maze)"),
-            ("prof_grid_final", "ncu_trace_grid", "trace_deposit_kernel on the 10 000-wall maze, RAR_FLAG_USE_GRID (RAR_GRID=1 tools/run_trace.py maze)"),
-            ("prof_cmac_final", "ncu_cmac", "stream_cmac_kernel on BASELINE config 5 (tools/run_trace.py conv)")]
-    for rep, name, title in jobs:
+    for rep, name, title in JOBS.get(tag, []):
         path = os.path.join(OUT, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue
@@ -69,10 +79,10 @@ def main():
             f.write(f"# ncu --set full --clock-control none --import-source on: {title}\n{raw(path)}\n\n"
                     "# per-source-line warp instructions (with inlining one SASS instruction is attributed to every line of its\n"
                     "# inline chain, so the per-line counts overlap; the kernel total is smsp__inst_executed.sum above)\n" + lines)
-    lc = os.path.join(OUT, "launches_final.csv")
+    lc = os.path.join(OUT, "launches_final.csv" if tag == "r01_final" else f"{tag}_launches.csv")
     if os.path.exists(lc):
         with open(os.path.join(PROF, f"{tag}_launches_summary.txt"), "w") as f:
-            f.write(launches(lc, "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1") + "\n")
+            f.write(launches(lc, "ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 2 --warmup 3") + "\n")
         with open(lc) as src, open(os.path.join(PROF, f"{tag}_launches.csv"), "w") as dst:
             dst.write(src.read())
 
