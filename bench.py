@@ -6,17 +6,17 @@ convolved samples/s).
 
 One JSON line on stdout (rank 0).  A "step" is one IR build of BASELINE config 2 (synthetic shoebox,
 4 walls, 1 Mi rays x 32 bounces, 1 s IR at 48 kHz): clear the histogram slot, trace + deposit, and
--- for N > 1 -- one NCCL all-reduce of the int64 histogram.  Each rank traces its own contiguous ray-id
-range of a dispatch of N x 1 Mi rays (weak scaling).  The same line carries the convolution stage
+-- for N > 1 -- one all-reduce of the int64 histogram (the library's peer-memory kernel).  Each rank traces its share
+of a dispatch of N x 1 Mi rays (weak scaling): chunks rank, rank + N, ... of 2^14 contiguous ray ids.  The same line carries the convolution stage
 (config 5: 256 streams x 10 s IRs per GPU, block 256) under "conv", a large-scene trace (config 3
 geometry, reduced ray count) under "maze", the roofline of the dominant kernel and the CPU baseline.
 
 Legs added for the multi-GPU record (N >= 1, same launch): `strong.c3` -- BASELINE config 3 geometry (10 000 walls,
-8 bands, 64 bounces, brute force) with a FIXED total of 4 849 664 rays split over the N ranks by contiguous ray-id
-range, two-shot all-reduce of the 3.07 MB histogram -- and `strong.c2` -- config 2 with a fixed total of 1 Mi rays
+8 bands, 64 bounces, brute force) with a FIXED total of 4 849 664 rays split over the N ranks in block-cyclic chunks of
+contiguous ray ids, two-shot all-reduce of the 3.07 MB histogram -- and `strong.c2` -- config 2 with a fixed total of 1 Mi rays
 (the latency regime).  Both compare the SHA-256 of the all-reduced histogram with the hash the CPU oracle minted for
 the unsharded dispatch (tests/golden/strong_scaling.json): `parity_ok`.  `unsharded_equal` does the same for the weak
-leg against a single-GPU trace of all N ranges.
+leg against a single-GPU trace of the whole dispatch.
 
 `--impl reference` times the CPU oracle (the only CPU implementation of this path that exists: the
 reference itself is HLSL compute run by Unity) on the host cores, on bounded samples of the same
@@ -43,6 +43,7 @@ WORKLOAD = "config2: synthetic shoebox 10x6 m (4 walls), 1048576 rays x 32 bounc
 RAYS_PER_GPU = 1 << 20
 BOUNCES = 32
 FLOPS_PER_TEST = 20.0  # ~20 fp32 lane-ops per ray-segment test
+CHUNK_LOG2 = 14        # N > 1: a rank traces chunks rank, rank + N, ... of 2^14 contiguous ray ids (rar_trace_interleaved)
 IR_BINS = 48000
 
 
@@ -213,14 +214,21 @@ def run_ours(args):
     # ---- workload ------------------------------------------------------------------------------
     sc = scenes.shoebox(ray_count=RAYS_PER_GPU * world, max_bounces=BOUNCES)
     n_bins = sc.impulse_length
-    lo, hi = sharding.shard_range(RAYS_PER_GPU * world, rank, world)
     ctx.set_walls(sc.walls)
     ctx.ir_clear(0, n_bins, 1)
     hist_t = sharding.DeviceHistogram(ctx, 0, dev).tensor
 
     def params(frame, flags=0):
         return _capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
-                                       BOUNCES, frame, sc.ray_count, 100, sc.sample_rate, n_bins, 1, 1.0, flags, lo, hi)
+                                       BOUNCES, frame, sc.ray_count, 100, sc.sample_rate, n_bins, 1, 1.0, flags, 0, 0)
+
+    def trace(frame, slot, flags=0):
+        """This rank's share of the dispatch of N x 1 Mi rays: block-cyclic chunks of contiguous ray ids (one contiguous
+        range per rank leaves the rank whose angular sector faces the listener 13 % behind the others)."""
+        if world == 1:
+            ctx.trace(params(frame, flags), slot)
+        else:
+            ctx.trace_interleaved(params(frame, flags), slot, rank, world, CHUNK_LOG2)
 
     # The all-reduce of the ray-range sharding: the library's own kernel over CUDA-IPC peer memory (the process
     # group only delivers the handles); RAR_BENCH_EXCHANGE=nccl selects ncclAllReduce on the same buffer instead.
@@ -243,7 +251,7 @@ def run_ours(args):
 
     def step(frame, nccl=use_nccl):
         ctx.ir_clear(0, n_bins, 1)
-        ctx.trace(params(frame), 0)
+        trace(frame, 0)
         exchange(nccl)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -259,14 +267,14 @@ def run_ours(args):
     ctx.get_counters(reset=True)
     for f in frames:
         ctx.ir_clear(0, n_bins, 1)
-        ctx.trace(params(f, _capi.RAR_FLAG_COUNT_TESTS), 0)
+        trace(f, 0, _capi.RAR_FLAG_COUNT_TESTS)
     c = ctx.get_counters(reset=True)
     tests_total = c["nearest_tests"] + c["shadow_tests"]
     # ... and the tests the production kernel actually evaluates (shadow rays whose estimate cannot clear the
     # deposit threshold are skipped): the honest numerator of the roofline's "achieved".
     for f in frames:
         ctx.ir_clear(0, n_bins, 1)
-        ctx.trace(params(f, _capi.RAR_FLAG_COUNT_TESTS | _capi.RAR_FLAG_COUNT_EXECUTED), 0)
+        trace(f, 0, _capi.RAR_FLAG_COUNT_TESTS | _capi.RAR_FLAG_COUNT_EXECUTED)
     c = ctx.get_counters(reset=True)
     tests_executed = c["nearest_tests"] + c["shadow_tests"]
 
@@ -333,7 +341,7 @@ def run_ours(args):
             s = k & 1
             ctx.set_walls(walls_host)                      # H2D: 40 B per wall
             ctx.ir_clear(s, n_bins, 1)
-            ctx.trace(params(frame), s)
+            trace(frame, s)
             if world > 1:
                 if use_nccl:
                     sharding.allreduce_histogram(hist_ts[s])
@@ -514,18 +522,14 @@ def check_unsharded(env, sc, params, step, hist_t, n_bins):
     equal = True
     if rank == 0:
         ctx.ir_clear(1, n_bins, 1)
-        total = RAYS_PER_GPU * world
-        for r in range(world):
-            lo, hi = env["sharding"].shard_range(total, r, world)
-            ctx.trace(capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
-                                             BOUNCES, frame, sc.ray_count, 100, sc.sample_rate, n_bins, 1, 1.0, 0, lo, hi), 1)
+        ctx.trace(params(frame), 1)                       # the whole dispatch of N x 1 Mi rays, unsharded, on this GPU alone
         equal = bool(np.array_equal(ctx.ir_read_fixed(1, n_bins), mine)) and bool(mine.any())
     digests = [_sha(mine)]
     if world > 1:
         digests = [None] * world
         dist.all_gather_object(digests, _sha(mine))
     return {"equal": _all_true(env, equal), "ranks_identical": len(set(digests)) == 1, "hist_sha256": digests[0],
-            "what": f"all-reduced histogram of {world} x {RAYS_PER_GPU} rays (frame {frame}) == rank 0 tracing all {world} ranges alone"}
+            "what": f"all-reduced histogram of {world} x {RAYS_PER_GPU} rays (frame {frame}, block-cyclic shards) == rank 0 tracing the whole dispatch alone"}
 
 
 STRONG_LEGS = {   # must equal tests/golden/make_strong_golden.py LEGS
@@ -535,7 +539,7 @@ STRONG_LEGS = {   # must equal tests/golden/make_strong_golden.py LEGS
 
 
 def bench_strong(env):
-    """STRONG scaling: a fixed dispatch split over the N ranks by contiguous ray-id range, one all-reduce of the
+    """STRONG scaling: a fixed dispatch split over the N ranks in block-cyclic chunks of ray ids, one all-reduce of the
     histogram per step.  c3 = BASELINE config 3 geometry (10 000-wall maze, 8 bands, 64 bounces, brute force) with
     4 849 664 rays in total; c2 = config 2 with 1 Mi rays in total (latency regime).  The SHA-256 of the all-reduced
     histogram is compared with the one the CPU oracle produced for the unsharded dispatch."""
@@ -553,27 +557,32 @@ def bench_strong(env):
         else:
             sc = scenes.shoebox(ray_count=leg["rays"], max_bounces=leg["bounces"])
         n, bands, slot = sc.impulse_length, leg["bands"], leg["slot"]
-        lo, hi = env["sharding"].shard_range(leg["rays"], rank, world)
         ctx.set_walls(sc.walls)
         if bands > 1:
             ctx.set_wall_band_absorption(sc.band_absorption)
         ctx.ir_clear(slot, n, bands)
         hist_t = env["sharding"].DeviceHistogram(ctx, slot, env["dev"]).tensor if (world > 1 and use_nccl) else None
 
-        def prm(flags=0, b=lo, e=hi, bounces=leg["bounces"]):
+        def prm(flags=0, b=0, e=0, bounces=leg["bounces"]):
             return capi.make_trace_params(sc.source, sc.listener, sc.listener_radius, sc.speed_of_sound, sc.input_gain,
                                           bounces, leg["frame"], leg["rays"], 0, sc.sample_rate, n, bands, 1.0, flags, b, e)
 
+        def trace_share(flags=0):
+            if world == 1:
+                ctx.trace(prm(flags), slot)
+            else:
+                ctx.trace_interleaved(prm(flags), slot, rank, world, CHUNK_LOG2)
+
         def one_step():
             ctx.ir_clear(slot, n, bands)
-            ctx.trace(prm(), slot)
+            trace_share()
             if world > 1:
                 if use_nccl:
                     env["sharding"].allreduce_histogram(hist_t)
                 else:
                     ex.allreduce(slot)
 
-        ctx.trace(prm(b=lo, e=min(hi, lo + 4096), bounces=2), slot)      # first launch of this kernel variant
+        ctx.trace(prm(b=0, e=4096, bounces=2), slot)                      # first launch of this kernel variant
         one_step()                                                        # warm-up at full size
         env["barrier"]()
         evs = []
@@ -590,14 +599,15 @@ def bench_strong(env):
         # the tests the production kernel evaluates on this rank's share (roofline numerator)
         ctx.get_counters(reset=True)
         ctx.ir_clear(slot, n, bands)
-        ctx.trace(prm(capi.RAR_FLAG_COUNT_TESTS | capi.RAR_FLAG_COUNT_EXECUTED), slot)
+        trace_share(capi.RAR_FLAG_COUNT_TESTS | capi.RAR_FLAG_COUNT_EXECUTED)
         c = ctx.get_counters(reset=True)
         (ms,) = _max_over_ranks(env, [ms])
         (executed,) = _sum_over_ranks(env, [c["nearest_tests"] + c["shadow_tests"]])
         tests = g["counters"]["nearest_tests"] + g["counters"]["shadow_tests"]
         parity = _all_true(env, digest == g["hist_sha256"])
         res = {"workload": f"{sc.name}: {leg['walls']} walls, {leg['rays']} rays in total x {leg['bounces']} bounces, {bands} band(s), "
-                           f"brute force; ray ids split over {world} GPU(s), all-reduce of {n * bands * 8} bytes",
+                           f"brute force; ray ids split over {world} GPU(s) in block-cyclic chunks of {1 << CHUNK_LOG2}, "
+                           f"all-reduce of {n * bands * 8} bytes",
                "n_gpus": world, "ir_build_ms": ms, "steps": leg["reps"], "tests": tests, "tests_executed": executed,
                "tests_per_s": tests / (ms * 1e-3), "tests_executed_per_s": executed / (ms * 1e-3),
                "hist_sha256": digest, "golden_sha256": g["hist_sha256"], "parity_ok": parity,

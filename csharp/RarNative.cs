@@ -79,6 +79,7 @@ namespace Rar2D
         [DllImport(Lib)] public static extern int rar_exchange_destroy(IntPtr ctx);
 
         [DllImport(Lib)] public static extern int rar_trace(IntPtr ctx, ref RarTraceParams p, int slot);
+        [DllImport(Lib)] public static extern int rar_trace_interleaved(IntPtr ctx, ref RarTraceParams p, int slot, int rank, int world, int chunkLog2);
         [DllImport(Lib)] public static extern int rar_trace_frames(IntPtr ctx, ref RarTraceParams p, int slot, int nFrames);
         [DllImport(Lib)] public static extern int rar_trace_listeners(IntPtr ctx, ref RarTraceParams p, [In] float[] listenersXY, int nListeners, int firstSlot);
         [DllImport(Lib)] public static extern int rar_trace_hits(IntPtr ctx, ref RarTraceParams p, IntPtr hits, IntPtr keys, long capacity, out long count);

@@ -81,6 +81,7 @@ SYMBOLS = {
     "rar_prepare_clips": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64]),
     "rar_prepare_clips_device": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64]),
     "rar_trace": (C.c_int, [_p, C.POINTER(TraceParams), _i32]),
+    "rar_trace_interleaved": (C.c_int, [_p, C.POINTER(TraceParams), _i32, _i32, _i32, _i32]),
     "rar_trace_frames": (C.c_int, [_p, C.POINTER(TraceParams), _i32, _i32]),
     "rar_trace_listeners": (C.c_int, [_p, C.POINTER(TraceParams), _p, _i32, _i32]),
     "rar_trace_hits": (C.c_int, [_p, C.POINTER(TraceParams), _p, _p, _i64, C.POINTER(_i64)]),
@@ -313,6 +314,10 @@ class Context:
     # trace ------------------------------------------------------------------------------------
     def trace(self, params: TraceParams, slot: int) -> None:
         self._ck(self._lib.rar_trace(self._h, C.byref(params), slot))
+
+    def trace_interleaved(self, params: TraceParams, slot: int, rank: int, world: int, chunk_log2: int = 14) -> None:
+        """rar_trace_interleaved: this rank's block-cyclic share (chunks of 2^chunk_log2 thread ids) of the dispatch."""
+        self._ck(self._lib.rar_trace_interleaved(self._h, C.byref(params), slot, rank, world, chunk_log2))
 
     def trace_frames(self, params: TraceParams, slot: int, n_frames: int) -> None:
         self._ck(self._lib.rar_trace_frames(self._h, C.byref(params), slot, n_frames))

@@ -1077,9 +1077,24 @@ int rar_prepare_clips(rar_context *ctx, const float *raw, int64_t samples, int32
 
 // ---- trace ------------------------------------------------------------------------------------------
 
-static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames);
+struct Interleave {
+    int world = 1, rank = 0, shift = 0;
+};
+static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames, Interleave il = Interleave());
 
 int rar_trace(rar_context *ctx, const rar_trace_params *params, int32_t slot) { return trace_frames_impl(ctx, params, slot, 1); }
+
+int rar_trace_interleaved(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t rank, int32_t world, int32_t chunk_log2) {
+    if (world < 1 || rank < 0 || rank >= world || chunk_log2 < 5 || chunk_log2 > 30)
+        return fail(ctx, RAR_ERR_INVALID, "need 0 <= rank < world and chunks of 2^5 .. 2^30 thread ids");
+    if (params && (params->ray_begin != 0 || params->ray_end != 0))
+        return fail(ctx, RAR_ERR_INVALID, "rar_trace_interleaved shards the whole dispatch: ray_begin / ray_end must be 0");
+    Interleave il;
+    il.world = world;
+    il.rank = rank;
+    il.shift = chunk_log2;
+    return trace_frames_impl(ctx, params, slot, 1, il);
+}
 
 int rar_trace_frames(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames) {
     if (n_frames < 0) return fail(ctx, RAR_ERR_INVALID, "n_frames must be >= 0");
@@ -1087,7 +1102,7 @@ int rar_trace_frames(rar_context *ctx, const rar_trace_params *params, int32_t s
     return trace_frames_impl(ctx, params, slot, n_frames);
 }
 
-static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames) {
+static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, int32_t slot, int32_t n_frames, Interleave il) {
     RAR_ENTER(ctx);
     int rc = check_trace_params(ctx, params);
     if (rc != RAR_OK) return rc;
@@ -1101,6 +1116,18 @@ static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, i
     if (rc != RAR_OK) return rc;
     a.hist = reinterpret_cast<unsigned long long *>(S->d_hist);
     a.n_frames = n_frames;
+    if (il.world > 1) {
+        // this rank's chunks: c = rank, rank + world, ... below ceil(total / chunk); the launch indexes them densely
+        const long long total = a.ray_end, chunk = 1LL << il.shift;
+        const long long chunks = (total + chunk - 1) / chunk;
+        const long long mine = chunks > il.rank ? (chunks - il.rank + il.world - 1) / il.world : 0;
+        a.cyc_world = il.world;
+        a.cyc_rank = il.rank;
+        a.cyc_shift = il.shift;
+        a.cyc_total = total;
+        a.ray_begin = 0;
+        a.ray_end = mine << il.shift;
+    }
     const bool count = (params->flags & RAR_FLAG_COUNT_TESTS) != 0;
     a.counters = count ? ctx->d_counters.p : nullptr;
     if (params->debug_ray_count > 0) {
@@ -1110,7 +1137,7 @@ static int trace_frames_impl(rar_context *ctx, const rar_trace_params *params, i
         // clear of the buffer; a launch that does not cover all rows (a ray-range shard) clears it the old way.
         if ((size_t)entries > ctx->d_debug.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // growth frees a buffer in use
         RAR_CUDA(ctx, ctx->d_debug.reserve((size_t)entries));
-        if (a.ray_begin > 0 || a.ray_end < rows)
+        if (a.ray_begin > 0 || a.ray_end < rows || a.cyc_world > 1)
             RAR_CUDA(ctx, cudaMemsetAsync(ctx->d_debug.p, 0, (size_t)entries * sizeof(f4), ctx->stream));
         ctx->debug_entries = (int)entries;
         a.debug_rays = ctx->d_debug.p;

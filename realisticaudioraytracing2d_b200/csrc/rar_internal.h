@@ -23,6 +23,11 @@ struct TraceLaunch {
     RayConsts p;
     long long ray_begin, ray_end;
     int n_frames;  // >= 1: frames rng_state_offset .. +n_frames-1 of the same dispatch traced by one launch
+    // block-cyclic sharding (rar_trace_interleaved): cyc_world > 1 maps launch index i to dispatch thread id
+    // ((i >> shift) * world + rank) << shift | (i & mask); ids >= cyc_total do not exist.  [ray_begin, ray_end) is then
+    // the launch's own index range, starting at 0.
+    int cyc_world, cyc_rank, cyc_shift;
+    long long cyc_total;
     unsigned long long *hist;  // [impulse_length][bands] Q23.40, nullptr in hit-list mode
     rar_ray_info *hits;        // hit-list mode outputs
     rar_hit_key *keys;

@@ -185,14 +185,47 @@ __device__ __forceinline__ void deposit_lane(const TraceLaunch &a, unsigned long
 }
 
 // The direct listener crossing of a bounce (Raytrace2D.compute:74-84) is rare -- one warp-bounce in ten holds one on
-// config 2, in one or two lanes -- so it is deposited where it is found, inside the live-ray region, with a plain
-// atomic: no vote, no reconvergence point (the aggregated path cost 14 issue slots per warp-bounce just to find out
-// that nobody had one).
+// config 2 -- so it is deposited where it is found, inside the live-ray region: no full-mask vote and no reconvergence
+// point on the other nine (the convergent path cost 14 issue slots per warp-bounce just to find out that nobody had
+// one).  But when it happens it usually happens to the whole warp (adjacent rays follow the same mirror path and cross
+// the listener together, into the same bin), and 32 atomics on one address serialise in one L2 slice: the rank whose
+// ray sector faces the listener ran 13 % longer than the others.  So the lanes that meet here aggregate
+// opportunistically: whoever is converged at this point (__activemask) matches bins and sums shared ones before the
+// atomic.  Any grouping gives the same integer total, so the histogram stays deterministic.
 template <int BANDS>
 __device__ __forceinline__ void deposit_direct(const TraceLaunch &a, unsigned long long *hist, const Arrival<BANDS> &h) {
     if (!h.has) return;
     const int bin = time_bin(h.t, a.p.sample_rate_f, a.p.time_divisor, a.p.impulse_length_f, a.p.impulse_length);
-    if (bin >= 0) deposit_lane<BANDS>(a, hist, h, bin);
+    if (bin < 0) return;
+    const unsigned here = __activemask();
+    const unsigned peers = __match_any_sync(here, bin);
+    if ((peers & (peers - 1)) == 0) {  // alone in its bin
+        deposit_lane<BANDS>(a, hist, h, bin);
+        return;
+    }
+    const bool leader = (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1);
+    if (BANDS == 1) {
+        long long q = quantize_energy(h.e);
+        if (!fits_two_limbs(h.e)) {
+            if (q != 0) atomicAdd(hist + bin, (unsigned long long)q);
+            q = 0;
+        }
+        q = group_sum_q2(peers, q);
+        if (leader && q != 0) atomicAdd(hist + bin, (unsigned long long)q);
+    } else {
+        unsigned long long *row = hist + (size_t)bin * a.band_total + a.band_offset;
+#pragma unroll
+        for (int b = 0; b < BANDS; b++) {
+            if (b >= a.band_valid) break;  // short last chunk of a banded slot
+            long long q = quantize_energy(h.band_e[b]);
+            if (!fits_two_limbs(h.band_e[b])) {
+                if (q != 0) atomicAdd(row + b, (unsigned long long)q);
+                q = 0;
+            }
+            q = group_sum_q2(peers, q);
+            if (leader && q != 0) atomicAdd(row + b, (unsigned long long)q);
+        }
+    }
 }
 
 // Warp-convergent aggregated deposit (the next-event arrivals: up to 32 per warp-bounce, adjacent rays share bins).
@@ -391,7 +424,13 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
         const long long idx = base + threadIdx.x;
         bool alive = idx < n_rays;
         const uint32_t frame = a.n_frames > 1 ? (uint32_t)(idx / rays_per_frame) : 0u;
-        const uint32_t id = (uint32_t)(a.ray_begin + (a.n_frames > 1 ? idx - (long long)frame * rays_per_frame : idx));
+        uint32_t id = (uint32_t)(a.ray_begin + (a.n_frames > 1 ? idx - (long long)frame * rays_per_frame : idx));
+        if (a.cyc_world > 1) {
+            // block-cyclic shard (rar_trace_interleaved): chunk k of this launch is chunk k * world + rank of the dispatch
+            const long long g = (((idx >> a.cyc_shift) * a.cyc_world + a.cyc_rank) << a.cyc_shift) + (idx & ((1LL << a.cyc_shift) - 1));
+            alive = alive && g < a.cyc_total;
+            id = (uint32_t)g;
+        }
         RayState<BANDS> r;
         if (alive) ray_init(r, id, a.p, frame);
 

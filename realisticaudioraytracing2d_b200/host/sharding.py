@@ -25,6 +25,15 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def interleaved_chunks(total: int, rank: int, world: int, chunk_log2: int):
+    """The [begin, end) id ranges rar_trace_interleaved(rank, world, chunk_log2) traces of a dispatch of `total` thread
+    ids: chunks rank, rank + world, ... of 2^chunk_log2 ids (the last chunk of the dispatch may be short)."""
+    if world <= 0 or not (0 <= rank < world) or total < 0 or chunk_log2 < 0:
+        raise ValueError("bad shard arguments")
+    chunk = 1 << chunk_log2
+    return [(c * chunk, min((c + 1) * chunk, total)) for c in range(rank, -(-total // chunk), world)]
+
+
 def dispatched_threads(ray_count: int, exact: bool = False) -> int:
     """Threads the reference's Trace dispatch runs: ceil(rayCount/64)*64 unless `exact`
     (Raytrace2D.compute:49-52, Helpers/ComputeHelper.cs:27-31)."""

@@ -111,6 +111,25 @@ def test_ray_range_sharding_is_bit_identical(ctx, oracle):
     assert np.array_equal(ctx.ir_read_fixed(1, n), whole)
 
 
+@pytest.mark.parametrize("world,chunk_log2", [(2, 10), (3, 5), (8, 12), (8, 14)])
+def test_block_cyclic_sharding_is_bit_identical(ctx, oracle, world, chunk_log2):
+    """rar_trace_interleaved: every rank's share (chunks rank, rank + world, ... of 2^k thread ids) accumulated into one
+    slot is the unsharded histogram; a dispatch that is not a multiple of the chunk, and more ranks than chunks."""
+    sc = scenes.smoll_room()
+    kw = trace_kwargs(sc, ray_count=15000 if chunk_log2 < 14 else 5000)
+    n = kw["impulse_length"]
+    ctx.set_walls(sc.walls)
+    ctx.ir_clear(0, n, 1)
+    for r in range(world):
+        ctx.trace_interleaved(capi_params(_capi, kw), 0, r, world, chunk_log2)
+    want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw)).hist
+    assert np.array_equal(ctx.ir_read_fixed(0, n), want)
+    with pytest.raises(_capi.RarError):
+        ctx.trace_interleaved(capi_params(_capi, dict(kw, ray_begin=0, ray_end=64)), 0, 0, world, chunk_log2)
+    with pytest.raises(_capi.RarError):
+        ctx.trace_interleaved(capi_params(_capi, kw), 0, world, world, chunk_log2)
+
+
 def test_exact_ray_count_flag_and_dispatch_rounding(ctx, oracle):
     sc = scenes.smoll_room()
     for flags in (0, _capi.RAR_FLAG_EXACT_RAY_COUNT):

@@ -88,3 +88,18 @@ def test_load_sample_mono_mix_and_resample():
     assert len(out) == 480                                          # RoundToInt(samples / ratio) (:153)
     ratio = np.float32(44100) / np.float32(48000)
     assert np.allclose(out, np.minimum(np.arange(480, dtype=np.float32) * ratio, 440), atol=1e-3)
+
+
+def test_interleaved_chunks_partition_the_dispatch():
+    from realisticaudioraytracing2d_b200.host.sharding import interleaved_chunks
+    for total, world, k in [(15040, 8, 12), (15040, 3, 5), (1 << 20, 8, 14), (100, 4, 5), (0, 2, 6), (4849664, 8, 14)]:
+        seen = np.zeros(total, np.int32)
+        sizes = []
+        for r in range(world):
+            ranges = interleaved_chunks(total, r, world, k)
+            sizes.append(sum(e - b for b, e in ranges))
+            for b, e in ranges:
+                assert b % (1 << k) == 0 and 0 < e - b <= (1 << k)
+                seen[b:e] += 1
+        assert np.all(seen == 1)                                   # every thread id exactly once
+        assert max(sizes) - min(sizes) <= (1 << k)                 # shares differ by at most one chunk
