@@ -661,7 +661,7 @@ def bench_listeners(env):
     ctx.ir_clear(first + per_gpu, n, 1)
     ctx.trace(prm(listener=(float(mine[k, 0]), float(mine[k, 1]))), first + per_gpu)
     single = ctx.ir_read_fixed(first + per_gpu, n)
-    same = bool(np.array_equal(single, heads[k])) and bool(heads[k].any())
+    same = bool(np.array_equal(single, heads[k]))        # (a rank whose listeners all hear nothing compares two empty histograms)
     if not same:
         sys.stderr.write(f"[bench] listeners: listener {k} fused nonzero {np.count_nonzero(heads[k])} sum {int(heads[k].sum())}; "
                          f"single nonzero {np.count_nonzero(single)} sum {int(single.sum())}\n")
@@ -671,12 +671,12 @@ def bench_listeners(env):
     c = ctx.get_counters(reset=True)
     executed = c["nearest_tests"] + c["shadow_tests"]
     (ms,) = _max_over_ranks(env, [ms])
-    (executed_all,) = _sum_over_ranks(env, [executed])
+    executed_all, reached_all = _sum_over_ranks(env, [executed, reached])
     res = {"workload": f"config4 share: {per_gpu} listeners per GPU x {rays} rays x {bounces} bounces, {walls}-wall scene, "
                        f"{n} bins per listener, fused listener kernel (each ray traced once per launch)",
            "n_gpus": world, "listeners_total": per_gpu * world, "ms": ms, "ms_per_listener": ms / per_gpu,
            "tests_executed": executed_all, "tests_executed_per_s": executed_all / (ms * 1e-3),
-           "listeners_with_arrivals_rank0": reached, "fused_equals_single_listener_trace": _all_true(env, same)}
+           "listeners_with_arrivals": int(reached_all), "fused_equals_single_listener_trace": _all_true(env, same)}
     if env["fp32_peak"]:
         ach = executed * FLOPS_PER_TEST / (ms * 1e-3) / 1e12
         res["roofline"] = {"bound": "fp32-issue", "achieved": ach, "peak": env["fp32_peak"] / 1e12, "unit": "Tlaneop/s",
