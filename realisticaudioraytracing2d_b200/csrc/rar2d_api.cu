@@ -306,6 +306,7 @@ void fill_launch(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     a.band_valid = p->bands > 8 ? 8 : p->bands;
     a.p = ray_consts(*p);
     a.opaque = ctx->walls_are_opaque ? 1 : 0;
+    a.tile_counter = ctx->d_counters.p + 6;  // words 0-4: test counters, 5: hit count, 6: tile counter
     a.spec_ok = spec_ranges_ok(*p, ctx->walls_are_bounded, ctx->walls_are_opaque) ? 1 : 0;
     ray_range(*p, a.ray_begin, a.ray_end);
 }

@@ -34,6 +34,7 @@ struct TraceLaunch {
     long long hit_cap;
     unsigned long long *hit_count;
     unsigned long long *counters;  // 5 words (rar_counters) or nullptr
+    unsigned long long *tile_counter;  // one word the launch code zeroes: CTAs claim their further ray tiles from it
     f4 *debug_rays;                // max(100, debug_ray_count) * (max_bounce_count+1) or nullptr
     int debug_ray_count;
     int debug_capacity;            // entries in debug_rays

@@ -420,8 +420,17 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
     const int max_b = a.p.max_bounce_count;
     RayCounters ctr = {0, 0, 0, 0, 0};
 
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_rays; base += (long long)gridDim.x * blockDim.x) {
-        const long long idx = base + threadIdx.x;
+    // Tiles of 32 consecutive rays, one warp each.  A warp's first tile is its own global index; further tiles are
+    // claimed from a counter in global memory (a.tile_counter, zeroed before the launch) instead of a fixed stride: rays
+    // differ in cost (a maze ray's shadow walks end anywhere between wall 1 and wall 10 000), so a fixed assignment
+    // leaves the slowest warp of the launch behind the mean.  Claiming per WARP keeps the warps of a CTA independent
+    // of each other (a per-CTA claim needs a block-wide barrier per tile, which cost the 1024-thread kernels 6 %).
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile * 32 < n_rays;) {
+        const long long idx = tile * 32 + lane;
+        long long next_tile = tile + warps_total;
+        if (a.tile_counter != nullptr && lane == 0)  // claimed now, used after this tile: the atomic's latency is hidden
+            next_tile = warps_total + (long long)atomicAdd(a.tile_counter, 1ull);
         bool alive = idx < n_rays;
         const uint32_t frame = a.n_frames > 1 ? (uint32_t)(idx / rays_per_frame) : 0u;
         uint32_t id = (uint32_t)(a.ray_begin + (a.n_frames > 1 ? idx - (long long)frame * rays_per_frame : idx));
@@ -506,6 +515,7 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
                 deposit_hist<BANDS, (STAGE != 0 || GRID)>(a, a.hist, nee, lane);
             }
         }
+        tile = a.tile_counter != nullptr ? __shfl_sync(kFull, next_tile, 0) : next_tile;
     }
 
     if (COUNT && a.counters != nullptr) {
@@ -849,6 +859,13 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
         arg.band_total = arg.bands;
         arg.band_offset = 0;
         arg.band_valid = arg.bands;
+    }
+    if (arg.n_listeners > 0 || want <= cap) arg.tile_counter = nullptr;  // one tile per warp (or the listener kernel): nothing to claim
+    if (const char *nd = getenv("RAR_NO_DYNAMIC_TILES"))                  // A/B measurements: fixed stride over the tiles
+        if (nd[0] == '1') arg.tile_counter = nullptr;
+    if (arg.tile_counter != nullptr) {
+        e = cudaMemsetAsync(arg.tile_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
     }
     void *params[] = {&arg};
     e = cudaLaunchKernel(k.fn, dim3(grid), dim3(threads), params, smem, stream);
