@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from realisticaudioraytracing2d_b200 import scenes
 from realisticaudioraytracing2d_b200.host.sharding import (allreduce_histogram, dispatched_threads, gather_handles,
-                                                           shard_range)
+                                                           interleaved_chunks, shard_range)
 from tests.common import oracle_params, oracle_walls, trace_kwargs
 
 
@@ -27,6 +27,13 @@ def _worker(rank, world, port, out_dir):
     t = torch.from_numpy(part.copy())
     allreduce_histogram(t)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), t.numpy())
+    # the block-cyclic shard bench.py uses at N > 1 (rar_trace_interleaved): chunks rank, rank + world, ... of 2^8 ids
+    part = np.zeros_like(part)
+    for lo, hi in interleaved_chunks(dispatched_threads(3000), rank, world, 8):
+        part += O.trace(oracle_walls(O, sc.walls), oracle_params(O, dict(kw, ray_begin=lo, ray_end=hi)), n_threads=2).hist
+    t = torch.from_numpy(part.copy())
+    allreduce_histogram(t)
+    np.save(os.path.join(out_dir, f"cyclic{rank}.npy"), t.numpy())
     # the transport of the peer-memory exchange's handles: rank order, every rank sees all of them
     handles = gather_handles(bytes([rank]) * 80)
     assert handles == [bytes([r]) * 80 for r in range(world)]
@@ -42,6 +49,7 @@ def test_two_rank_allreduce_is_bit_identical_to_one_rank(tmp_path, oracle):
     whole = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, trace_kwargs(sc, ray_count=3000))).hist
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"rank{r}.npy"), whole)
+        assert np.array_equal(np.load(tmp_path / f"cyclic{r}.npy"), whole)
 
 
 class _StubContext:
