@@ -24,13 +24,14 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 UNITS = [
     ("trace_kernel.cu", ["--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
     ("conv_kernels.cu", []),
+    ("band_synth.cu", []),
     ("exchange_kernel.cu", []),
     ("clip_kernel.cu", ["--fmad=false", "-prec-div=true", "-ftz=false"]),
     ("ring.cu", []),
     ("grid_kernel.cu", ["--fmad=false"]),
     ("rar2d_api.cu", []),
 ]
-HEADERS = ["rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_layout.h", "rar_internal.h", "../../include/rar2d.h"]
+HEADERS = ["rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_synth16.cuh", "rar_layout.h", "rar_internal.h", "../../include/rar2d.h"]
 
 
 def _nvcc() -> str:

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -13,6 +14,7 @@
 
 #include "rar_internal.h"
 #include "rar_layout.h"
+#include "rar_synth16.cuh"
 
 using namespace rar;
 
@@ -154,6 +156,8 @@ struct rar_context {
     DevBuf<float> d_synth;  // synthesised broadband response (scratch)
     PinnedBuf<float> h_band_taps;
     DevBuf<float> d_band_taps;
+    PinnedBuf<float2> h_band_T;  // tables of the production synthesis kernel (rar_synth16.cuh synth_tables)
+    DevBuf<float2> d_band_T;
     DevBuf<unsigned long long> d_counters;  // 5 counters + 1 hit count
     DevBuf<f4> d_debug;
     int debug_entries = 0;
@@ -362,8 +366,24 @@ int ensure_band_filters(rar_context *ctx, int bands) {
     // one partition per band: H[b] = rfft512([g_b, 0 ...])
     RAR_CUDA(ctx, launch_ir_spectra(ctx->d_band_taps.p, (int)taps, ctx->d_band_G.p, bands, kBlock, ctx->stream));
     ctx->launches++;
+    if (band_synth16_applicable(bands, 1)) {
+        const size_t len = synth_table_len(bands);
+        RAR_CUDA(ctx, ctx->h_band_T.reserve(len));
+        RAR_CUDA(ctx, ctx->d_band_T.reserve(len));
+        synth_tables(ctx->h_band_taps.p, bands, reinterpret_cast<f2 *>(ctx->h_band_T.p));
+        RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_band_T.p, ctx->h_band_T.p, len * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->band_G_bands = bands;
     return RAR_OK;
+}
+
+// Synthesis of a batch of banded slots of one shape: the register-transform kernel where it applies
+// (RAR_NO_FAST_SYNTH=1 keeps the generic shared-memory kernel, for A/B measurements and tests).
+cudaError_t synth_batch(rar_context *ctx, const BandSynthBatch &batch, int n_items, int bins, int bands, int stride, int out_len) {
+    static const bool no_fast = [] { const char *e = getenv("RAR_NO_FAST_SYNTH"); return e && e[0] == '1'; }();
+    if (!no_fast && band_synth16_applicable(bands, stride))
+        return launch_band_synth16(batch, n_items, bins, bands, ctx->d_band_T.p, out_len, ctx->stream);
+    return launch_band_synth(batch, n_items, bins, bands, stride, ctx->d_band_G.p, out_len, ctx->stream);
 }
 
 // Samples of the broadband response a slot stands for: bins x samples per bin.
@@ -391,7 +411,7 @@ int slot_response(rar_context *ctx, Slot &S, float scale, float *d_out) {
     std::memset(&batch, 0, sizeof batch);
     batch.items[0] = BandSynthItem{S.d_hist, d_out, scale, 0};
     RAR_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(float), ctx->stream));
-    RAR_CUDA(ctx, launch_band_synth(batch, 1, S.impulse_length, S.bands, S.time_stride, ctx->d_band_G.p, n, ctx->stream));
+    RAR_CUDA(ctx, synth_batch(ctx, batch, 1, S.impulse_length, S.bands, S.time_stride, n));
     ctx->launches++;
     return RAR_OK;
 }
@@ -508,6 +528,8 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_synth.release();
     ctx->h_band_taps.release();
     ctx->d_band_taps.release();
+    ctx->h_band_T.release();
+    ctx->d_band_T.release();
     ctx->d_grid_start.release();
     ctx->d_grid_items.release();
     ctx->d_grid_geo.release();
@@ -1604,7 +1626,7 @@ int rar_conv_set_irs_from_slots(rar_convolver *cv, int32_t first_stream, int32_t
                                                acc > 0 ? 1.0f / (float)acc : 0.0f, 0};
             }
             RAR_CUDA(ctx, cudaMemsetAsync(d, 0, (size_t)g * row * sizeof(float), ctx->stream));
-            RAR_CUDA(ctx, launch_band_synth(batch, g, S0->impulse_length, S0->bands, S0->time_stride, ctx->d_band_G.p, (int)ir_len, ctx->stream));
+            RAR_CUDA(ctx, synth_batch(ctx, batch, g, S0->impulse_length, S0->bands, S0->time_stride, (int)ir_len));
             ctx->launches++;
         } else {
             for (int k = 0; k < g; k++) {

@@ -123,6 +123,11 @@ struct BandSynthBatch {
 };
 cudaError_t launch_band_synth(const BandSynthBatch &batch, int n_items, int bins, int bands, int stride, const float2 *G, int out_len,
                               cudaStream_t s);
+// The production kernel for bands % 4 == 0 on the sample grid (band_synth.cu): same result within the 1e-4 contract.
+// T = the tables of rar_synth16.cuh synth_tables (twiddles and the zero-phase amplitudes of the band filters).
+bool band_synth16_applicable(int bands, int stride);
+cudaError_t launch_band_synth16(const BandSynthBatch &batch, int n_items, int bins, int bands, const float2 *T, int out_len,
+                                cudaStream_t s);
 
 // One-shot convolution (AudioConvolve semantics):
 //  X[j] = rfft([x[(j-1)B .. jB), x[jB .. (j+1)B)]) with |x| <= 1e-4 zeroed, j in [0, n_xwin)

@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "_build", "libhost_emulation.so")
 _SRC = os.path.join(_HERE, "host_emulation.cpp")
 _DEPS = [_SRC] + [os.path.join(_ROOT, "realisticaudioraytracing2d_b200", "csrc", h)
-                  for h in ("rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_layout.h")]
+                  for h in ("rar_math.cuh", "rar_ray.cuh", "rar_fft.cuh", "rar_synth16.cuh", "rar_layout.h")]
 
 
 def build(force: bool = False) -> str:
@@ -82,6 +82,23 @@ def convolve(x, ir, accum):
     ir = np.ascontiguousarray(ir, np.float32)
     out = np.zeros(len(x) + len(ir), np.float32)
     lib().emu_convolve(C.c_void_p(x.ctypes.data), len(x), C.c_void_p(ir.ctypes.data), len(ir), int(accum), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def fft16(x, inverse=False, half=False):
+    v = np.ascontiguousarray(x, np.complex64).copy()
+    lib().emu_fft16(C.c_void_p(v.ctypes.data), int(inverse), int(half))
+    return v
+
+
+def band_synth16(hist, bands, scale, taps, out_len):
+    """Filter-bank synthesis with the arithmetic of csrc/band_synth.cu (rar_synth16.cuh) on the host."""
+    hist = np.ascontiguousarray(hist, np.int64)
+    taps = np.ascontiguousarray(taps, np.float32)
+    assert taps.shape == (bands, 256)
+    out = np.zeros(out_len, np.float32)
+    lib().emu_band_synth16(C.c_void_p(hist.ctypes.data), len(hist) // bands, int(bands), C.c_float(scale), C.c_void_p(taps.ctypes.data),
+                           C.c_void_p(out.ctypes.data), int(out_len))
     return out
 
 

@@ -199,6 +199,78 @@ void irfft512(const rar::f2 *P, float *w) {  // w = 256 * true inverse
 extern "C" __attribute__((visibility("default"))) void emu_rfft512(const float *w, float *P) { rfft512(w, (rar::f2 *)P); }
 extern "C" __attribute__((visibility("default"))) void emu_irfft512(const float *P, float *w) { irfft512((const rar::f2 *)P, w); }
 
+// ---- filter-bank synthesis with the 16 x 16 register transforms of rar_synth16.cuh (band_synth.cu's arithmetic) ----
+#include "../realisticaudioraytracing2d_b200/csrc/rar_synth16.cuh"
+
+extern "C" __attribute__((visibility("default")))
+void emu_fft16(float *x /*16 complex*/, int inverse, int half) {
+    rar::f2 v[16];
+    std::memcpy(v, x, sizeof v);
+    if (inverse) { if (half) rar::fft16<true, true>(v); else rar::fft16<true, false>(v); }
+    else { if (half) rar::fft16<false, true>(v); else rar::fft16<false, false>(v); }
+    std::memcpy(x, v, sizeof v);
+}
+
+// out[n] += sum_b (g_b * h_b)[n + 127], h_b[n] = hist[n*bands + b] * 2^-40 * scale; taps [bands][256]
+extern "C" __attribute__((visibility("default")))
+void emu_band_synth16(const long long *hist, int bins, int bands, float scale, const float *taps, float *out, int out_len) {
+    using rar::f2;
+    std::vector<f2> T(rar::synth_table_len(bands));
+    rar::synth_tables(taps, bands, T.data());
+    const f2 *tw = T.data(), *w2 = T.data() + 256, *wt = T.data() + 512;
+    const int n_seg = (bins + 255) / 256;
+    for (int p = 0; p < n_seg; p++) {
+        const long long first = (long long)p * 256;
+        f2 U[16][16], W[16][16], buf[16][16];
+        std::memset(U, 0, sizeof U);
+        std::memset(W, 0, sizeof W);
+        for (int b = 0; b < bands; b++) {
+            for (int t = 0; t < 16; t++) {  // stage 1: thread t holds z[t + 16 r], r < 8
+                f2 y[16];
+                for (int r = 0; r < 8; r++) {
+                    const long long g = first + 2 * (t + 16 * r);
+                    const float a = g < bins ? ((float)hist[g * bands + b] * 9.094947017729282e-13f) * scale : 0.0f;
+                    const float c = g + 1 < bins ? ((float)hist[(g + 1) * bands + b] * 9.094947017729282e-13f) * scale : 0.0f;
+                    y[r] = f2{a, c};
+                }
+                rar::fft16<false, true>(y);
+                for (int k1 = 0; k1 < 16; k1++) buf[k1][t] = k1 ? rar::cmul(y[k1], tw[t * 16 + k1]) : y[k1];
+            }
+            for (int k1 = 0; k1 < 16; k1++) {  // stage 2: thread k1 holds Z[k1 + 16 k2]
+                f2 v[16], ab[16];
+                for (int t = 0; t < 16; t++) v[t] = buf[k1][t];
+                rar::fft16<false, false>(v);
+                for (int k2 = 0; k2 < 16; k2++) ab[k2] = wt[(size_t)b * 256 + k1 * 16 + k2];
+                rar::synth_accumulate(U[k1], W[k1], v, ab);
+            }
+        }
+        for (int t = 0; t < 16; t++) {  // partner exchange, merge, inverse stage 1
+            f2 Up[16], Wp[16], w[16], Zp[16];
+            const int src = (16 - t) & 15;
+            for (int k2 = 0; k2 < 16; k2++) {
+                const int reg = t == 0 ? (16 - k2) & 15 : 15 - k2;
+                Up[k2] = U[src][reg];
+                Wp[k2] = W[src][reg];
+                w[k2] = w2[t * 16 + k2];
+            }
+            rar::synth_merge(t, U[t], W[t], Up, Wp, w, Zp);
+            rar::fft16<true, false>(Zp);
+            for (int n2 = 0; n2 < 16; n2++) buf[n2][t] = n2 ? rar::cmul(Zp[n2], rar::conj2(tw[t * 16 + n2])) : Zp[n2];
+        }
+        for (int n2 = 0; n2 < 16; n2++) {  // inverse stage 2: thread n2 holds z'[n2 + 16 n1]
+            f2 v[16];
+            for (int k1 = 0; k1 < 16; k1++) v[k1] = buf[n2][k1];
+            rar::fft16<true, false>(v);
+            for (int n1 = 0; n1 < 16; n1++) {
+                const int m = 2 * (n2 + 16 * n1);
+                const long long o = first + (m < 384 ? m : m - 512);
+                if (o >= 0 && o < out_len) out[o] += v[n1].x * (1.0f / 256.0f);
+                if (o + 1 >= 0 && o + 1 < out_len) out[o + 1] += v[n1].y * (1.0f / 256.0f);
+            }
+        }
+    }
+}
+
 // The one-shot pipeline of rar_convolve_begin: input windows, per-block CMAC over partitions, output blocks.
 extern "C" __attribute__((visibility("default")))
 void emu_convolve(const float *x, int x_len, const float *ir, int ir_len, int accum, float *out) {

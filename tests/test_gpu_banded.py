@@ -52,6 +52,20 @@ def test_equal_bands_synthesise_to_their_common_response(ctx, oracle):
     assert rel_l2(got, want) <= 2e-6
 
 
+@pytest.mark.parametrize("n,bands", [(100, 8), (256, 4), (257, 8), (2047, 12), (2048, 8), (2049, 4), (5000, 20)])
+def test_register_transform_synthesis_shapes(ctx, oracle, n, bands):
+    """band_synth.cu (bands a multiple of 4): segment tails, responses shorter than a segment, partially filled
+    CTAs (eight segments each) and chunk counts other than two."""
+    rng = np.random.default_rng(n + bands)
+    ir = (rng.random((n, bands)) * (rng.random((n, bands)) < 0.3) * 2e-3).astype(np.float32)
+    ir[0] = 1e-3
+    ir[-1] = 3e-3
+    ctx.ir_write(58, ir.ravel(), bands=bands)
+    hist = ctx.ir_read_fixed(58, n * bands)
+    want = oracle.synthesize_ir(hist, n, bands)
+    assert rel_l2(ctx.synthesize_ir(58, n), want) <= 3e-6
+
+
 @pytest.mark.parametrize("bands,edges_hz", [(3, None), (8, [0, 88, 177, 354, 707, 1414, 2828, 5657, 24000]), (128, None)])
 def test_band_counts_and_custom_edges(ctx, oracle, bands, edges_hz):
     """Other band counts (WindowSize = 128 is the experimental variant's default, RayTraceManagerComplex.cs:27) and
