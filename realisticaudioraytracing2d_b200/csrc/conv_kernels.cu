@@ -10,6 +10,7 @@
 // stream per block).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -535,6 +536,8 @@ cudaError_t launch_ir_spectra_batch(const float *ir_f, long long ir_stride, int 
                                     int n_items, int block, cudaStream_t s) {
     if (block != kB) return cudaErrorInvalidValue;
     if (n_part <= 0 || n_items <= 0) return cudaSuccess;
+    static const bool no_fast = [] { const char *e = getenv("RAR_NO_FAST_SYNTH"); return e && e[0] == '1'; }();
+    if (!no_fast && ir_spectra16_applicable(ir_f, ir_stride)) return launch_ir_spectra16(ir_f, ir_stride, ir_len, H, h_stride, n_part, n_items, s);
     ir_spectra_kernel<<<dim3(blocks_for(n_part, kSub), n_items), 64 * kSub, 0, s>>>(ir_f, ir_stride, ir_len, reinterpret_cast<f2 *>(H),
                                                                                      h_stride, n_part);
     return cudaGetLastError();

@@ -382,7 +382,8 @@ int ensure_band_filters(rar_context *ctx, int bands) {
 cudaError_t synth_batch(rar_context *ctx, const BandSynthBatch &batch, int n_items, int bins, int bands, int stride, int out_len) {
     static const bool no_fast = [] { const char *e = getenv("RAR_NO_FAST_SYNTH"); return e && e[0] == '1'; }();
     if (!no_fast && band_synth16_applicable(bands, stride))
-        return launch_band_synth16(batch, n_items, bins, bands, ctx->d_band_T.p, out_len, ctx->stream);
+        return launch_band_synth16(batch, n_items, bins, bands, ctx->d_band_T.p, out_len, ctx->d_counters.p + 7, ctx->dev.sm_count,
+                                   ctx->stream);  // (d_counters words 0-4: test counters, 5: hit count, 6: ray tiles, 7: synthesis work)
     return launch_band_synth(batch, n_items, bins, bands, stride, ctx->d_band_G.p, out_len, ctx->stream);
 }
 
@@ -480,6 +481,7 @@ int rar_create(int device, rar_context **out) {
     ctx->stream = ctx->own_stream;
     ctx->slots.resize(2);  // ping / pong, RayTraceManager.cs:36
     conv_init_tables(ctx->own_stream);
+    synth_init_tables(ctx->own_stream);
     e = ctx->d_counters.reserve(8);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), ctx->own_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);  // creation-time initialisation is complete on return

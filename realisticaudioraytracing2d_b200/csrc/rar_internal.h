@@ -126,8 +126,14 @@ cudaError_t launch_band_synth(const BandSynthBatch &batch, int n_items, int bins
 // The production kernel for bands % 4 == 0 on the sample grid (band_synth.cu): same result within the 1e-4 contract.
 // T = the tables of rar_synth16.cuh synth_tables (twiddles and the zero-phase amplitudes of the band filters).
 bool band_synth16_applicable(int bands, int stride);
-cudaError_t launch_band_synth16(const BandSynthBatch &batch, int n_items, int bins, int bands, const float2 *T, int out_len,
+// Partition spectra with the same register transforms (ir 8-byte aligned, even stride); synth_init_tables once per device.
+void synth_init_tables(cudaStream_t stream);
+bool ir_spectra16_applicable(const float *ir_f, long long ir_stride);
+cudaError_t launch_ir_spectra16(const float *ir_f, long long ir_stride, int ir_len, float2 *H, long long h_stride, int n_part, int n_items,
                                 cudaStream_t s);
+// counter: 8 bytes of device memory the launch may use (work distribution; zeroed by the launcher on the stream).
+cudaError_t launch_band_synth16(const BandSynthBatch &batch, int n_items, int bins, int bands, const float2 *T, int out_len,
+                                unsigned long long *counter, int sm_count, cudaStream_t s);
 
 // One-shot convolution (AudioConvolve semantics):
 //  X[j] = rfft([x[(j-1)B .. jB), x[jB .. (j+1)B)]) with |x| <= 1e-4 zeroed, j in [0, n_xwin)

@@ -12,7 +12,8 @@
 // the packed transform Z_b by the split step P[k] = alpha_k Z[k] + beta_k conj(Z[M-k]).  Z[M-k] lives in another
 // thread, so instead of splitting every band the kernel accumulates two sums with REAL weights on its own elements,
 //        U[k] = sum_b A_b[k] Z_b[k],      W[k] = sum_b A_b[M-k] Z_b[k],
-// and does the exchange with the partner thread once per segment: S[k] = alpha_k U[k] + beta_k conj(W[M-k]).
+// and does the exchange with the partner thread once per segment: S[k] = alpha_k U[k] + beta_k conj(W[M-k]); composed
+// with the merge step of the inverse transform this collapses to three real multiples per bin (synth_merge1).
 // A_b is the zero-phase amplitude of band b's symmetric 255-tap filter (the filters are used centred; the 512-point
 // circular convolution then wraps the 127 samples before the segment to the end of the window, which the output
 // step unwraps), so the weights are real and a band costs 4 FMAs per element.
@@ -113,40 +114,39 @@ RAR_HD f2 synth_split(f2 z, f2 zm, f2 w) {
     return cadd(xe, cmul(w, xo));
 }
 
-// Spectrum of the segment's synthesised window, ready for the inverse packed transform:
-// Zp[k2] = merge(S[k], S[M-k]) (irfft_merge of rar_fft.cuh), S[k] = alpha_k U[k] + beta_k conj(W[M-k]), k = t + 16 k2.
-// Up[k2] / Wp[k2] are the partner's sums at M-k; w2[k2] = exp(-2 pi i k / 512).
-RAR_HD void synth_merge(int t, const f2 (&U)[16], const f2 (&W)[16], const f2 (&Up)[16], const f2 (&Wp)[16], const f2 (&w2)[16],
-                        f2 (&Zp)[16]) {
-#pragma unroll
-    for (int k2 = 0; k2 < 16; k2++) {
-        const f2 w = w2[k2];
-        const f2 Sk = synth_split(U[k2], Wp[k2], w);
-        const f2 Sm = synth_split(Up[k2], W[k2], f2{-w.x, w.y});  // w at M-k = -conj(w)
-        const f2 xe = f2{0.5f * (Sk.x + Sm.x), 0.5f * (Sk.y - Sm.y)};
-        const f2 d = f2{0.5f * (Sk.x - Sm.x), 0.5f * (Sk.y + Sm.y)};
-        const f2 xo = cmul(d, conj2(w));
-        f2 z = f2{xe.x - xo.y, xe.y + xo.x};
-        if (k2 == 0 && t == 0) {  // packed bin 0 = (DC, Nyquist): DC = sum_b A_b[0] (Z.x + Z.y), Nyquist = sum_b A_b[M] (Z.x - Z.y)
-            const float x0 = U[0].x + U[0].y, xm = W[0].x - W[0].y;
-            z = f2{0.5f * (x0 + xm), 0.5f * (x0 - xm)};
-        }
-        Zp[k2] = z;
+// Spectrum of the segment's synthesised window, ready for the inverse packed transform, one bin k = t + 16 k2.
+// Composing the split step (rfft_split: S[k] = alpha U[k] + beta conj(W[M-k])) with the merge step of the inverse
+// (irfft_merge: Z'[k] = conj(alpha) S[k] + conj(beta) conj(S[M-k])), alpha = (1 - i w)/2, beta = (1 + i w)/2,
+// w = exp(-i theta), theta = 2 pi k / 512, and alpha_{M-k} = conj(alpha), beta_{M-k} = conj(beta):
+//        Z'[k] = |alpha|^2 U[k] + |beta|^2 W[k] + conj(alpha) beta conj(W[M-k]) + alpha conj(beta) conj(U[M-k])
+//              = (1 - sin theta)/2 U[k] + (1 + sin theta)/2 W[k] + i (cos theta)/2 conj(W[M-k] - U[M-k]).
+// Ep = W[M-k] - U[M-k] comes from the partner thread; w = (cos theta, -sin theta) from the table.
+// Bin 0 packs (DC, Nyquist): DC = sum_b A_b[0] (Z.x + Z.y) = U.x + U.y, Nyquist = sum_b A_b[M] (Z.x - Z.y) = W.x - W.y.
+RAR_HD f2 synth_merge1(bool first, f2 U, f2 W, f2 Ep, f2 w) {
+    const float a = fmaf(0.5f, w.y, 0.5f), b = 1.0f - a, h = 0.5f * w.x;
+    f2 z = f2{fmaf(a, U.x, fmaf(b, W.x, h * Ep.y)), fmaf(a, U.y, fmaf(b, W.y, h * Ep.x))};
+    if (first) {
+        const float x0 = U.x + U.y, xm = W.x - W.y;
+        z = f2{0.5f * (x0 + xm), 0.5f * (x0 - xm)};
     }
+    return z;
 }
 
-// Host side: the kernel's tables.  T[0..256): tw[t*16 + k1] = exp(-2 pi i t k1 / 256); T[256..512): w2[t*16 + k2] =
-// exp(-2 pi i (t + 16 k2) / 512); T[512 + b*256 + t*16 + k2] = (A_b[k], A_b[256 - k]), k = t + 16 k2, with
-// A_b[k] = sum_j g_b[j] cos(2 pi k (j - 127) / 512) the zero-phase amplitude of band b's filter (taps: [bands][256],
-// 255 taps and a zero).  synth_table_len(bands) f2 elements.
+// Tables.  A table row belongs to a thread t and holds 16 elements e; it is stored so that the 16 threads of a
+// transform read it with coalesced 16-byte loads: element e of thread t at f2 index synth_tab(t, e) of its 256-entry
+// table (the float4 of elements 2j, 2j+1 of all t is contiguous over t).
+// T[0..256): tw(t, k1) = exp(-2 pi i t k1 / 256); T[256..512): w2(t, k2) = exp(-2 pi i (t + 16 k2) / 512);
+// T[512 + b*256 ...): (A_b[k], A_b[256 - k]) at (t, k2), k = t + 16 k2, with A_b[k] = sum_j g_b[j] cos(2 pi k (j - 127) / 512)
+// the zero-phase amplitude of band b's filter (taps: [bands][256], 255 taps and a zero).  synth_table_len(bands) f2 elements.
+RAR_HD int synth_tab(int t, int e) { return (((e >> 1) * 16 + t) << 1) + (e & 1); }
 inline size_t synth_table_len(int bands) { return 512 + (size_t)bands * 256; }
 inline void synth_tables(const float *taps, int bands, f2 *T) {
     const double two_pi = 6.283185307179586476925286766559;
     for (int t = 0; t < 16; t++)
         for (int j = 0; j < 16; j++) {
             const double a = two_pi * (double)(t * j) / 256.0, b = two_pi * (double)(t + 16 * j) / 512.0;
-            T[t * 16 + j] = f2{(float)cos(a), (float)-sin(a)};
-            T[256 + t * 16 + j] = f2{(float)cos(b), (float)-sin(b)};
+            T[synth_tab(t, j)] = f2{(float)cos(a), (float)-sin(a)};
+            T[256 + synth_tab(t, j)] = f2{(float)cos(b), (float)-sin(b)};
         }
     double c512[512];
     for (int i = 0; i < 512; i++) c512[i] = cos(two_pi * (double)i / 512.0);
@@ -160,7 +160,7 @@ inline void synth_tables(const float *taps, int bands, f2 *T) {
         for (int t = 0; t < 16; t++)
             for (int k2 = 0; k2 < 16; k2++) {
                 const int k = t + 16 * k2;
-                T[512 + (size_t)b * 256 + t * 16 + k2] = f2{(float)A[k], (float)A[256 - k]};
+                T[512 + (size_t)b * 256 + synth_tab(t, k2)] = f2{(float)A[k], (float)A[256 - k]};
             }
     }
 }

@@ -234,28 +234,25 @@ void emu_band_synth16(const long long *hist, int bins, int bands, float scale, c
                     y[r] = f2{a, c};
                 }
                 rar::fft16<false, true>(y);
-                for (int k1 = 0; k1 < 16; k1++) buf[k1][t] = k1 ? rar::cmul(y[k1], tw[t * 16 + k1]) : y[k1];
+                for (int k1 = 0; k1 < 16; k1++) buf[k1][t] = k1 ? rar::cmul(y[k1], tw[rar::synth_tab(t, k1)]) : y[k1];
             }
             for (int k1 = 0; k1 < 16; k1++) {  // stage 2: thread k1 holds Z[k1 + 16 k2]
                 f2 v[16], ab[16];
                 for (int t = 0; t < 16; t++) v[t] = buf[k1][t];
                 rar::fft16<false, false>(v);
-                for (int k2 = 0; k2 < 16; k2++) ab[k2] = wt[(size_t)b * 256 + k1 * 16 + k2];
+                for (int k2 = 0; k2 < 16; k2++) ab[k2] = wt[(size_t)b * 256 + rar::synth_tab(k1, k2)];
                 rar::synth_accumulate(U[k1], W[k1], v, ab);
             }
         }
         for (int t = 0; t < 16; t++) {  // partner exchange, merge, inverse stage 1
-            f2 Up[16], Wp[16], w[16], Zp[16];
+            f2 Zp[16];
             const int src = (16 - t) & 15;
             for (int k2 = 0; k2 < 16; k2++) {
                 const int reg = t == 0 ? (16 - k2) & 15 : 15 - k2;
-                Up[k2] = U[src][reg];
-                Wp[k2] = W[src][reg];
-                w[k2] = w2[t * 16 + k2];
+                Zp[k2] = rar::synth_merge1(t == 0 && k2 == 0, U[t][k2], W[t][k2], rar::csub(W[src][reg], U[src][reg]), w2[rar::synth_tab(t, k2)]);
             }
-            rar::synth_merge(t, U[t], W[t], Up, Wp, w, Zp);
             rar::fft16<true, false>(Zp);
-            for (int n2 = 0; n2 < 16; n2++) buf[n2][t] = n2 ? rar::cmul(Zp[n2], rar::conj2(tw[t * 16 + n2])) : Zp[n2];
+            for (int n2 = 0; n2 < 16; n2++) buf[n2][t] = n2 ? rar::cmul(Zp[n2], rar::conj2(tw[rar::synth_tab(t, n2)])) : Zp[n2];
         }
         for (int n2 = 0; n2 < 16; n2++) {  // inverse stage 2: thread n2 holds z'[n2 + 16 n1]
             f2 v[16];
