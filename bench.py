@@ -818,7 +818,7 @@ def bench_config1(ctx, _capi, scenes, torch, stream):
 def bench_banded(env, peaks, peaks_kind):
     """banded responses into the streaming convolver.  16 streams, each taking its response from its own
     banded slot of 480 000 bins x 8 bands (a 10 s IR per band, 30.7 MB of Q23.40 words per slot, 491 MB in all, > L2):
-    filter-bank synthesis (band_synth_kernel) followed by the partition spectra (ir_spectra_kernel), per stream."""
+    filter-bank synthesis (band_synth16_kernel) followed by the partition spectra (ir_spectra16_kernel), per stream."""
     ctx, capi, scenes, torch, stream = env["ctx"], env["capi"], env["scenes"], env["torch"], env["stream"]
     S, n, bands, first = 16, 480000, 8, 300
     cv = capi.Convolver(ctx, S, 256, n)
@@ -853,7 +853,7 @@ def bench_banded(env, peaks, peaks_kind):
             "ms": ms, "ms_per_stream": ms / S, "responses_per_s": S / (ms * 1e-3), "impulse_check_rel_l2": err,
             "gpu_launches_per_step": 2,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": _traffic("band_synth_kernel"), "kernel": "band_synth_kernel", "peak_kind": peaks_kind,
+                         "traffic": _traffic("band_synth16_kernel"), "kernel": "band_synth16_kernel", "peak_kind": peaks_kind,
                          "algorithmic_bytes_per_launch": S * (n * bands * 8 + n * 4),
                          "note": "bytes of the whole step (response clear, synthesis, spectra) over its time; the synthesis "
                                  "kernel reads the 8-byte histogram words once and adds into the 4-byte response"}}

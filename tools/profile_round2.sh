@@ -15,7 +15,8 @@ run $ncu_full -k regex:trace_deposit -c 1 -s 1 -o $out/r02_maze8 -f $py tools/ru
 $py tools/run_trace.py c1 3 > $out/r02_plain_c1.log 2>&1 || exit 1
 run $ncu_full -k regex:trace_deposit -c 1 -s 2 -o $out/r02_c1 -f $py tools/run_trace.py c1 3 > $out/r02_ncu_c1.log 2>&1
 $py tools/run_bench_leg.py banded > $out/r02_plain_banded.log 2>&1 || exit 1
-run $ncu_full -k regex:band_synth -c 1 -s 2 -o $out/r02_band_synth -f $py tools/run_bench_leg.py banded > $out/r02_ncu_banded.log 2>&1
+run $ncu_full -k regex:band_synth16 -c 1 -s 2 -o $out/r02_band_synth16 -f $py tools/run_bench_leg.py banded > $out/r02_ncu_banded.log 2>&1
+RAR_NO_FAST_SYNTH=1 run $ncu_full -k regex:band_synth_kernel -c 1 -s 2 -o $out/r02_band_synth -f $py tools/run_bench_leg.py banded > $out/r02_ncu_banded_old.log 2>&1
 $py bench.py --steps 2 --warmup 3 > $out/r02_bench_for_launches.json 2> $out/r02_bench_for_launches.err || exit 1
 run ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/r02_launches.csv $py bench.py --steps 2 --warmup 3 > $out/r02_ncu_bench.log 2>&1
 ls -la $out/r02_* >&2
