@@ -38,6 +38,10 @@ struct Slot {
     int H_cap = 0;  // partitions allocated
     int H_parts = 0;
     bool H_valid = false;
+    // rar_ir_read_begin converts and copies on the context's read stream; whoever touches the histogram next on the
+    // main stream waits for it (get_slot)
+    cudaEvent_t read_done = nullptr;
+    bool read_pending = false;
 };
 
 template <class T>
@@ -87,6 +91,7 @@ struct Ticket {
     bool failed = false;
     int out_len = 0;
     cudaEvent_t done = nullptr;
+    cudaEvent_t ready = nullptr;  // ir_read: recorded on the main stream, awaited by the read stream
     PinnedBuf<float> h_in, h_out;
     DevBuf<float> d_x, d_out;
     DevBuf<float2> d_X, d_Y;
@@ -119,19 +124,21 @@ static_assert(kExMaxRanks == RAR_EXCHANGE_MAX_RANKS, "rank limit");
 struct rar_context {
     int device = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t read_stream = nullptr;  // conversion + device-to-host copy of rar_ir_read_begin: overlaps the next trace
     cudaStream_t stream = nullptr;
     DeviceFacts dev{};
     std::string err;
     long long launches = 0;
 
     // walls
-    DevBuf<f4> d_geo, d_mat0;
-    DevBuf<f2> d_mat1;
+    DevBuf<f4> d_planes;  // geo | mat0 | (mat1, end): one allocation, one upload per rar_set_walls
+    struct PlaneF4 { f4 *p = nullptr; void release() { p = nullptr; } } d_geo, d_mat0;   // views into d_planes
+    struct PlaneF2 { f2 *p = nullptr; void release() { p = nullptr; } } d_mat1;
     DevBuf<float> d_band_abs;
     int n_walls = -1;  // -1: never set
     int band_rows = 0, band_count = 0;
     std::vector<float> air;  // air absorption per band, 1/m (empty: none); rar_set_air_absorption
-    DevBuf<f2> d_end;                  // wall end points (the grid builder needs them unrounded)
+    PlaneF2 d_end;                     // wall end points (the grid builder needs them unrounded)
     PinnedBuf<f4> h_planes;            // pinned staging of the geo | mat0 | mat1 | end planes of one upload
     cudaEvent_t walls_uploaded = nullptr;  // the staging buffer may be rewritten once this has completed
     PinnedBuf<float> h_bands;          // pinned staging of the band-absorption table
@@ -220,7 +227,12 @@ Slot *get_slot(rar_context *ctx, int slot, bool create) {
         if (!create) return nullptr;
         ctx->slots.resize(slot + 1);
     }
-    return &ctx->slots[slot];
+    Slot *S = &ctx->slots[slot];
+    if (S->read_pending) {  // an asynchronous read of this slot may still be in flight on the read stream
+        cudaStreamWaitEvent(ctx->stream, S->read_done, 0);
+        S->read_pending = false;
+    }
+    return S;
 }
 
 int check_trace_params(rar_context *ctx, const rar_trace_params *p) {
@@ -323,6 +335,7 @@ Ticket *get_ticket(rar_context *ctx, int id) {
 void free_ticket(Ticket *t) {
     if (!t) return;
     if (t->done) cudaEventDestroy(t->done);
+    if (t->ready) cudaEventDestroy(t->ready);
     t->h_in.release();
     t->h_out.release();
     t->d_x.release();
@@ -338,7 +351,9 @@ int acquire_ticket(rar_context *ctx) {
         if (!ctx->tickets[i]->active) return (int)i;
     Ticket *t = new (std::nothrow) Ticket();
     if (!t) return fail(ctx, RAR_ERR_NOMEM, "out of host memory");
-    if (cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming) != cudaSuccess) {
+    if (cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming) != cudaSuccess) {
+        if (t->done) cudaEventDestroy(t->done);
         delete t;
         return fail(ctx, RAR_ERR_CUDA, "cudaEventCreate failed");
     }
@@ -473,8 +488,10 @@ int rar_create(int device, rar_context **out) {
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     ctx->dev.sm_clock_khz = khz;
-    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&ctx->read_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
+        if (ctx->read_stream) cudaStreamDestroy(ctx->read_stream);
         delete ctx;
         return fail(nullptr, RAR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
@@ -487,6 +504,7 @@ int rar_create(int device, rar_context **out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);  // creation-time initialisation is complete on return
     if (e != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
+        cudaStreamDestroy(ctx->read_stream);
         delete ctx;
         return fail(nullptr, RAR_ERR_CUDA, "counter allocation: %s", cudaGetErrorString(e));
     }
@@ -500,12 +518,14 @@ int rar_destroy(rar_context *ctx) {
     if (!ctx) return RAR_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->read_stream) cudaStreamSynchronize(ctx->read_stream);
     rar_exchange_destroy(ctx);
     while (!ctx->convolvers.empty()) rar_conv_destroy(ctx->convolvers.back());
     for (Ticket *t : ctx->tickets) free_ticket(t);
     for (Slot &s : ctx->slots) {
         if (s.d_hist) cudaFree(s.d_hist);
         if (s.d_H) cudaFree(s.d_H);
+        if (s.read_done) cudaEventDestroy(s.read_done);
     }
     ctx->h_planes.release();
     ctx->h_bands.release();
@@ -515,6 +535,7 @@ int rar_destroy(rar_context *ctx) {
     if (ctx->walls_uploaded) cudaEventDestroy(ctx->walls_uploaded);
     if (ctx->bands_uploaded) cudaEventDestroy(ctx->bands_uploaded);
     if (ctx->listeners_uploaded) cudaEventDestroy(ctx->listeners_uploaded);
+    ctx->d_planes.release();
     ctx->d_geo.release();
     ctx->d_mat0.release();
     ctx->d_mat1.release();
@@ -536,6 +557,7 @@ int rar_destroy(rar_context *ctx) {
     ctx->d_grid_items.release();
     ctx->d_grid_geo.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->read_stream) cudaStreamDestroy(ctx->read_stream);
     delete ctx;
     return RAR_OK;
 }
@@ -552,6 +574,7 @@ int rar_set_stream(rar_context *ctx, void *cuda_stream) {
 int rar_sync(rar_context *ctx) {
     RAR_ENTER(ctx);
     RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RAR_CUDA(ctx, cudaStreamSynchronize(ctx->read_stream));  // (its work was enqueued behind the main stream's)
     return RAR_OK;
 }
 
@@ -575,15 +598,14 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
     std::memset(h_geo, 0, pad * 3 * sizeof(f4));
     split_walls(segments, n, h_geo, h_mat0, h_mat1);
     for (int w = 0; w < n; w++) h_end[w] = f2{segments[w].end[0], segments[w].end[1]};
-    RAR_CUDA(ctx, ctx->d_geo.reserve(pad));
-    RAR_CUDA(ctx, ctx->d_mat0.reserve(pad));
-    RAR_CUDA(ctx, ctx->d_mat1.reserve(pad));
-    RAR_CUDA(ctx, ctx->d_end.reserve(pad));
-    // The previous planes may still be read by an enqueued trace; stream order makes the copies safe.
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_geo.p, h_geo, pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat0.p, h_mat0, pad * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mat1.p, h_mat1, pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_end.p, h_end, pad * sizeof(f2), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, ctx->d_planes.reserve(pad * 3));  // (growth frees the old planes: cudaFree waits for the device)
+    ctx->d_geo.p = ctx->d_planes.p;
+    ctx->d_mat0.p = ctx->d_geo.p + pad;
+    ctx->d_mat1.p = reinterpret_cast<f2 *>(ctx->d_mat0.p + pad);
+    ctx->d_end.p = ctx->d_mat1.p + pad;
+    // The previous planes may still be read by an enqueued trace; stream order makes the copy safe.  The device
+    // planes mirror the staging layout, so the whole scene is ONE host-to-device copy.
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_planes.p, h_geo, pad * 3 * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
     RAR_CUDA(ctx, cudaEventRecord(ctx->walls_uploaded, ctx->stream));
     if (n != ctx->n_walls) {
         ctx->band_rows = 0;
@@ -771,12 +793,19 @@ int rar_ir_read_begin(rar_context *ctx, int32_t slot, int64_t n, int32_t *ticket
     RAR_CUDA(ctx, T.h_out.reserve((size_t)n + 1));
     RAR_CUDA(ctx, T.d_out.reserve((size_t)n + 1));
     if (n > have) std::memset(T.h_out.p + have, 0, (size_t)(n - have) * sizeof(float));  // an unconfigured slot reads as zeros
+    // The read runs on its own stream behind everything enqueued so far, so that the next frame's work on ANOTHER slot
+    // (the ping/pong of RayTraceManager.cs:212-218) does not queue behind the conversion and the copy.
+    RAR_CUDA(ctx, cudaEventRecord(T.ready, ctx->stream));
+    RAR_CUDA(ctx, cudaStreamWaitEvent(ctx->read_stream, T.ready, 0));
     if (have > 0) {
-        RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, T.d_out.p, have, 1.0f, ctx->stream));
+        RAR_CUDA(ctx, launch_fixed_to_float(S->d_hist, T.d_out.p, have, 1.0f, ctx->read_stream));
         ctx->launches++;
-        RAR_CUDA(ctx, cudaMemcpyAsync(T.h_out.p, T.d_out.p, (size_t)have * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        RAR_CUDA(ctx, cudaMemcpyAsync(T.h_out.p, T.d_out.p, (size_t)have * sizeof(float), cudaMemcpyDeviceToHost, ctx->read_stream));
+        if (!S->read_done) RAR_CUDA(ctx, cudaEventCreateWithFlags(&S->read_done, cudaEventDisableTiming));
+        RAR_CUDA(ctx, cudaEventRecord(S->read_done, ctx->read_stream));
+        S->read_pending = true;
     }
-    RAR_CUDA(ctx, cudaEventRecord(T.done, ctx->stream));
+    RAR_CUDA(ctx, cudaEventRecord(T.done, ctx->read_stream));
     T.active = true;
     *ticket = id;
     return RAR_OK;

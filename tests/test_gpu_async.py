@@ -120,3 +120,27 @@ def test_band_table_update_is_ordered_behind_a_trace_in_flight(ctx, oracle):
     O = oracle
     assert np.array_equal(a, O.trace(oracle_walls(O, sc.walls), oracle_params(O, kw), band_abs=sc.band_absorption).hist)
     assert np.array_equal(b, O.trace(oracle_walls(O, sc.walls), oracle_params(O, kw), band_abs=other).hist)
+
+
+def test_async_reads_are_ordered_against_later_writes_of_the_same_slot(ctx, oracle):
+    """rar_ir_read_begin converts and copies on the context's read stream so that the next frame (other slot) does not
+    queue behind it.  A read in flight must still see the histogram as it was when the read was requested, whatever is
+    enqueued on the slot afterwards (clear, another trace), and reads of both slots may be in flight at once."""
+    sc = scenes.maze(n_segments=2000, ray_count=200_000, max_bounces=12, bands=1, seed=9)
+    n = sc.impulse_length
+    ctx.set_walls(sc.walls)
+    O = oracle
+    want = [O.trace(oracle_walls(O, sc.walls), oracle_params(O, trace_kwargs(sc, rng_state_offset=f))).hist for f in (1, 2, 3)]
+    for rep in range(3):
+        tickets = []
+        for k, f in enumerate((1, 2, 3)):
+            s = k & 1
+            ctx.ir_clear(s, n, 1)                            # (for k = 2: slot 0 again, while its first read may be in flight)
+            ctx.trace(capi_params(_capi, trace_kwargs(sc, rng_state_offset=f)), s)
+            tickets.append(ctx.ir_read_begin(s, n))
+        ctx.ir_clear(0, n, 1)                                # ... and cleared once more behind the last read
+        ctx.ir_clear(1, n, 1)
+        for k, t in enumerate(tickets):
+            got = ctx.ir_read_end(t, n)
+            assert np.array_equal(got, O.ir_to_float(want[k])), (rep, k)
+    assert not ctx.ir_read_fixed(0, n).any() and not ctx.ir_read_fixed(1, n).any()
