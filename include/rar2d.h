@@ -186,7 +186,9 @@ RAR_API int rar_ir_read(rar_context *ctx, int32_t slot, float *out, int64_t n);
  * (RayTraceManager.cs:114-121 does this for the convolution output): _begin enqueues the conversion and the copy
  * into pinned memory behind the work already on the stream and returns a ticket; rar_poll(ticket) tells whether it
  * has completed; _end waits if necessary, copies n values to `out` and releases the ticket.  Lets a host overlap
- * the next frame's upload and trace with this frame's readback. */
+ * the next frame's upload and trace with this frame's readback: the conversion and the copy run on a second stream
+ * of the context, behind everything enqueued before the call; a later call that touches the same slot is ordered
+ * behind the read, work on other slots (ping/pong) is not. */
 RAR_API int rar_ir_read_begin(rar_context *ctx, int32_t slot, int64_t n, int32_t *ticket);
 RAR_API int rar_ir_read_end(rar_context *ctx, int32_t ticket, float *out, int64_t n);
 
