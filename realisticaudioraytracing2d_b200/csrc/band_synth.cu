@@ -78,6 +78,10 @@ __device__ __forceinline__ void transpose16(f2 (*tr)[kTRow], int t, f2 (&y)[16],
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// bytes: a multiple of 16, p 16-byte aligned
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+}
 
 // ONE: at most eight bands, i.e. one staging group -- the sums are not live while the group is staged, so a lane
 // keeps sixteen loads in flight instead of eight.
@@ -159,7 +163,17 @@ band_synth16_kernel(const __grid_constant__ BandSynthBatch batch, int bins, int 
             }
             __syncwarp();
             if (c0 == 0) next = __shfl_sync(0xffffffffu, next, 0);
-            {   // L2 prefetch of what this warp stages next: the next group of this segment, or group 0 of the next pair
+            if (ONE && bands == kStage) {
+                // L2 prefetch of the next pair's words: with eight bands a segment is 16 KB of contiguous memory, one
+                // bulk prefetch issued by one lane
+                if (next < n_work && lane == 0) {
+                    const int nitem = next / n_seg, np = next - nitem * n_seg;
+                    const long long nfirst = (long long)np * 256;
+                    const int rows = (int)min((long long)256, (long long)bins - nfirst);
+                    prefetch_l2_bulk(batch.items[nitem].hist + nfirst * kStage, (unsigned)rows * 64u);
+                }
+            } else {
+                // ... in general: the next group of this segment, or group 0 of the next pair, row by row
                 const bool more = c0 + kStage < bands;
                 const int nitem = more ? item : next / n_seg, np = more ? p : next - nitem * n_seg;
                 if (more || next < n_work) {
