@@ -340,9 +340,11 @@ bool band_synth16_applicable(int bands, int stride) { return bands > 0 && bands 
 
 cudaError_t launch_band_synth16(const BandSynthBatch &batch, int n_items, int bins, int bands, const float2 *T, int out_len,
                                 unsigned long long *counter, int sm_count, cudaStream_t s) {
+    static std::mutex mu;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
+    std::unique_lock<std::mutex> lock(mu);  // contexts of several devices may be driven from several threads
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(band_synth16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SynthSmem));
         if (e == cudaSuccess)
@@ -350,6 +352,7 @@ cudaError_t launch_band_synth16(const BandSynthBatch &batch, int n_items, int bi
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
+    lock.unlock();
     for (int k = 0; k < n_items; k++)
         if ((reinterpret_cast<uintptr_t>(batch.items[k].out) & 7u) || (reinterpret_cast<uintptr_t>(batch.items[k].hist) & 15u))
             return cudaErrorMisalignedAddress;
