@@ -132,7 +132,7 @@ struct rar_context {
 
     // walls
     DevBuf<f4> d_planes;  // geo | mat0 | (mat1, end): one allocation, one upload per rar_set_walls
-    struct PlaneF4 { f4 *p = nullptr; void release() { p = nullptr; } } d_geo, d_mat0;   // views into d_planes
+    struct PlaneF4 { f4 *p = nullptr; void release() { p = nullptr; } } d_geo, d_mat0, d_pair_a, d_pair_b;   // views into d_planes
     struct PlaneF2 { f2 *p = nullptr; void release() { p = nullptr; } } d_mat1;
     DevBuf<float> d_band_abs;
     int n_walls = -1;  // -1: never set
@@ -312,6 +312,8 @@ int attach_grid(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
 void fill_launch(rar_context *ctx, const rar_trace_params *p, TraceLaunch &a) {
     std::memset(&a, 0, sizeof a);
     a.geo = ctx->d_geo.p;
+    a.pair_a = ctx->d_pair_a.p;
+    a.pair_b = ctx->d_pair_b.p;
     a.mat0 = ctx->d_mat0.p;
     a.mat1 = ctx->d_mat1.p;
     a.band_abs = p->bands > 1 ? ctx->d_band_abs.p : nullptr;
@@ -590,22 +592,26 @@ int rar_set_walls(rar_context *ctx, const rar_segment *segments, int32_t n) {
     // them; the next upload waits (normally not at all) for this one before it rewrites the staging buffer.
     if (ctx->walls_uploaded) RAR_CUDA(ctx, cudaEventSynchronize(ctx->walls_uploaded));
     else RAR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->walls_uploaded, cudaEventDisableTiming));
-    if (pad * 3 > ctx->h_planes.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // reallocation frees the old buffer
-    RAR_CUDA(ctx, ctx->h_planes.reserve(pad * 3));   // geo | mat0 | (mat1, end): two 8-byte planes share the third f4 plane
+    if (pad * 4 > ctx->h_planes.cap) RAR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // reallocation frees the old buffer
+    RAR_CUDA(ctx, ctx->h_planes.reserve(pad * 4));   // geo | mat0 | (mat1, end): two 8-byte planes share the third f4 plane | (pair_a, pair_b)
     f4 *h_geo = ctx->h_planes.p, *h_mat0 = h_geo + pad;
     f2 *h_mat1 = reinterpret_cast<f2 *>(h_mat0 + pad);
     f2 *h_end = h_mat1 + pad;
-    std::memset(h_geo, 0, pad * 3 * sizeof(f4));
+    f4 *h_pair_a = h_geo + 3 * pad, *h_pair_b = h_pair_a + pad / 2;   // pad / 2 >= (n + 1) / 2 records each
+    std::memset(h_geo, 0, pad * 4 * sizeof(f4));
     split_walls(segments, n, h_geo, h_mat0, h_mat1);
     for (int w = 0; w < n; w++) h_end[w] = f2{segments[w].end[0], segments[w].end[1]};
-    RAR_CUDA(ctx, ctx->d_planes.reserve(pad * 3));  // (growth frees the old planes: cudaFree waits for the device)
+    pair_planes(h_geo, n, h_pair_a, h_pair_b);
+    RAR_CUDA(ctx, ctx->d_planes.reserve(pad * 4));  // (growth frees the old planes: cudaFree waits for the device)
     ctx->d_geo.p = ctx->d_planes.p;
     ctx->d_mat0.p = ctx->d_geo.p + pad;
     ctx->d_mat1.p = reinterpret_cast<f2 *>(ctx->d_mat0.p + pad);
     ctx->d_end.p = ctx->d_mat1.p + pad;
+    ctx->d_pair_a.p = ctx->d_geo.p + 3 * pad;
+    ctx->d_pair_b.p = ctx->d_pair_a.p + pad / 2;
     // The previous planes may still be read by an enqueued trace; stream order makes the copy safe.  The device
     // planes mirror the staging layout, so the whole scene is ONE host-to-device copy.
-    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_planes.p, h_geo, pad * 3 * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
+    RAR_CUDA(ctx, cudaMemcpyAsync(ctx->d_planes.p, h_geo, pad * 4 * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
     RAR_CUDA(ctx, cudaEventRecord(ctx->walls_uploaded, ctx->stream));
     if (n != ctx->n_walls) {
         ctx->band_rows = 0;

@@ -47,6 +47,7 @@ struct TraceLaunch {
     GridView grid;
     int use_grid;
     int opaque;  // no wall has transmission > 0: kernels without the transmit/refract branch may be used
+    const f4 *pair_a, *pair_b;  // the endpoint plane as two-wall records (rar_layout.h pair_planes), for the PACKED kernels
     int spec_ok; // opaque, and every operand range the range-checked-once arithmetic assumes holds (spec_ranges_ok)
 };
 

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <vector>
 
 #include "../../include/rar2d.h"
@@ -25,6 +26,19 @@ inline void split_walls(const rar_segment *in, int n, f4 *geo, f4 *mat0, f2 *mat
         geo[w] = f4{s.start[0], s.start[1], ex, ey};
         mat0[w] = f4{s.normal[0], s.normal[1], s.absorption, s.scattering};
         mat1[w] = f2{s.transmission, s.ior};
+    }
+}
+
+// The endpoint plane once more, two walls per record, for the packed-FP32 wall tests (trace_kernel.cu, PACKED variants):
+// pair_a[p] = {x(2p), x(2p+1), y(2p), y(2p+1)}, pair_b[p] = {ex(2p), ex(2p+1), ey(2p), ey(2p+1)}; n_pairs = (n+1)/2.
+// A missing second wall gets NaN coordinates: every comparison of the filter is false for it, so it is never a survivor.
+inline void pair_planes(const f4 *geo, int n, f4 *pair_a, f4 *pair_b) {
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    for (int p = 0; 2 * p < n; p++) {
+        const f4 g0 = geo[2 * p];
+        const f4 g1 = 2 * p + 1 < n ? geo[2 * p + 1] : f4{nan, nan, nan, nan};
+        pair_a[p] = f4{g0.x, g1.x, g0.y, g1.y};
+        pair_b[p] = f4{g0.z, g1.z, g0.w, g1.w};
     }
 }
 

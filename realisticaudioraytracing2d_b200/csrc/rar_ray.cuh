@@ -154,6 +154,64 @@ RAR_HD bool wall_pass_unbounded(const WallTest &t) {
     return (fabsf(rar_fma(2.0f, t.num2, -t.dotP)) <= fabsf(t.dotP)) & forward;
 }
 
+// ---- packed wall tests (device only) ------------------------------------------------------------------------
+//
+// sm_100 has packed binary32 arithmetic (PTX fma/mul/add/sub .rn.f32x2 -> FFMA2 / FMUL2 / FADD2): one instruction, two
+// IEEE results, each rounded exactly like its scalar form.  Measured (tools/microbench.cu): a packed instruction
+// issues at half the rate of a scalar one, i.e. the same FP32 results per second for half the issue slots -- and the
+// wall scans are bound by issue slots (profiles/r02_phase_tables.txt).  The filter of two walls is evaluated in one
+// pass over a pair record (rar_layout.h pair_planes); the ray's constants enter as scalar operands, which the
+// hardware broadcasts to both halves.  Bit-identity with wall_test / wall_pass: the quantities are the same
+// expressions except for three sign conventions chosen so that no negation instruction is needed, each exact --
+//   nv1x = sx - ox = -(ox - sx),     ndotP = fma(ex, dy, ey * (-dx)) = -dotP,     nr = bound * ndotP = -r
+// (a product or an FMA of negated operands is the negated result in round-to-nearest) -- and the comparisons use
+// magnitudes only.  Where a zero's sign differs (x - x is +0 either way round) the result of the FILTER can only
+// differ for num1 = 0 or dotP = 0, which the exact evaluation rejects in both cases (t1 = 0 < eps, |dotP| < eps).
+#ifdef __CUDACC__
+struct WallTest2 {
+    uint64_t ndotP, num1, num2;  // (wall 2p, wall 2p+1)
+};
+__device__ __forceinline__ uint64_t pair_bc(float v) { return (uint64_t)__float_as_uint(v) | ((uint64_t)__float_as_uint(v) << 32); }
+__device__ __forceinline__ float pair_lo(uint64_t v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float pair_hi(uint64_t v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+template <class Scene>
+__device__ __forceinline__ WallTest2 wall_test2(const Scene &sc, int p, float ox, float oy, float dx, float ndy) {
+    uint64_t sx, sy, ex, ey;
+    sc.pair(p, sx, sy, ex, ey);
+    const uint64_t dy2 = pair_bc(-ndy), dx2 = pair_bc(dx);
+    const uint64_t nv1x = sub2(sx, pair_bc(ox));
+    const uint64_t v1y = sub2(pair_bc(oy), sy);
+    WallTest2 t;
+    t.ndotP = fma2(ex, dy2, mul2(ey, pair_bc(-dx)));
+    t.num2 = fma2(nv1x, dy2, mul2(v1y, dx2));
+    t.num1 = fma2(ex, v1y, mul2(ey, nv1x));
+    return t;
+}
+__device__ __forceinline__ void wall_pass2(const WallTest2 &t, float bound_m, bool &p0, bool &p1) {
+    const uint64_t two = pair_bc(2.0f);
+    const uint64_t nr = mul2(pair_bc(bound_m), t.ndotP);
+    const uint64_t c1 = fma2(two, t.num2, t.ndotP);  // 2 num2 - dotP
+    const uint64_t c2 = fma2(two, t.num1, nr);       // 2 num1 - r
+    p0 = (fabsf(pair_lo(c1)) <= fabsf(pair_lo(t.ndotP))) & (fabsf(pair_lo(c2)) <= fabsf(pair_lo(nr)));
+    p1 = (fabsf(pair_hi(c1)) <= fabsf(pair_hi(t.ndotP))) & (fabsf(pair_hi(c2)) <= fabsf(pair_hi(nr)));
+}
+#endif
+
 // ---- optional uniform grid over the walls (RAR_FLAG_USE_GRID) -------------------------------------------
 //
 // SURVEY.md 8(f)-2.  Brute force stays the default and the measured mode; the grid changes which walls are
@@ -318,6 +376,44 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
             hit = (W);                                               \
         }                                                            \
     }
+#define RAR_NEAREST_EXACT2(T, H, W)                                  \
+    {                                                                \
+        const float d = intersect_exact<Scene::kSpec>(pair_##H((T).num1), pair_##H((T).num2), -pair_##H((T).ndotP)); \
+        if (d < closest) {                                           \
+            closest = d;                                             \
+            closest_m = d * kSlack;                                  \
+            hit = (W);                                               \
+        }                                                            \
+    }
+#ifdef __CUDACC__
+    if constexpr (Scene::kPacked) {
+        // two pair records = four walls per iteration, in wall order (ties go to the lower index, as in the scalar scan)
+        const int np = (n + 1) >> 1;
+        int p = 0;
+        for (; p + 2 <= np; p += 2) {
+            const WallTest2 ta = wall_test2(sc, p, ox, oy, dx, ndy), tb = wall_test2(sc, p + 1, ox, oy, dx, ndy);
+            bool p0, p1, p2, p3;
+            wall_pass2(ta, closest_m, p0, p1);
+            wall_pass2(tb, closest_m, p2, p3);
+            if (p0 | p1 | p2 | p3) {
+                if (p0) RAR_NEAREST_EXACT2(ta, lo, 2 * p)
+                if (p1) RAR_NEAREST_EXACT2(ta, hi, 2 * p + 1)
+                if (p2) RAR_NEAREST_EXACT2(tb, lo, 2 * p + 2)
+                if (p3) RAR_NEAREST_EXACT2(tb, hi, 2 * p + 3)
+            }
+        }
+        if (p < np) {
+            const WallTest2 ta = wall_test2(sc, p, ox, oy, dx, ndy);
+            bool p0, p1;
+            wall_pass2(ta, closest_m, p0, p1);
+            if (p0) RAR_NEAREST_EXACT2(ta, lo, 2 * p)
+            if (p1) RAR_NEAREST_EXACT2(ta, hi, 2 * p + 1)
+        }
+        closest_out = closest;
+        hit_out = hit;
+        return;
+    }
+#endif
     if (Scene::kFixed4 || (Scene::kPeelFirstBatch && n >= 4)) {  // first batch: no bound yet
         const WallTest t0 = wall_test(sc.geo(0), ox, oy, dx, ndy);
         const WallTest t1 = wall_test(sc.geo(1), ox, oy, dx, ndy);
@@ -354,6 +450,7 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
         }
     }
 #undef RAR_NEAREST_EXACT
+#undef RAR_NEAREST_EXACT2
     closest_out = closest;
     hit_out = hit;
 }

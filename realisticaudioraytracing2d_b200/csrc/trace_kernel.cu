@@ -93,6 +93,9 @@ struct SceneView {
     static constexpr bool kGrid = GRID;
     static constexpr bool kSpec = (FAST & 1) != 0;
     static constexpr bool kFixed4 = (FAST & 2) != 0;
+    // the staged endpoint plane holds two walls per record (rar_layout.h pair_planes) and the wall scans run on packed
+    // FP32 instructions, two walls each (rar_ray.cuh "packed wall tests")
+    static constexpr bool kPacked = (FAST & 4) != 0;
     // small scenes (everything in shared memory, < kCoopMinWalls walls): the first filter batch of the
     // nearest-hit scan is peeled and uses the sign-aware filter (rar_ray.cuh wall_pass_unbounded); measured
     // -5.5 % on the 4-wall config 2, +6 % on the 10 000-wall maze when applied there too (code layout), so it
@@ -102,6 +105,7 @@ struct SceneView {
     const f4 *m0;
     const f2 *m1;
     uint32_t gs, m0s, m1s;  // shared-space addresses of the staged planes (STAGE 0: all three, STAGE 1: gs)
+    uint32_t pbs;           // kPacked: gs is pair_a, pbs is pair_b
     const float *ba;
     int n, nb, boff;
     GridView gv;
@@ -111,7 +115,21 @@ struct SceneView {
         return f4{v.x, v.y, v.z, v.w};
     }
     __device__ __forceinline__ int n_walls() const { return n; }
+    // pair record p: (x0 x1), (y0 y1) from pair_a; (ex0 ex1), (ey0 ey1) from pair_b -- one LDS.128 each
+    __device__ __forceinline__ void pair(int p, uint64_t &sx, uint64_t &sy, uint64_t &sz, uint64_t &sw) const {
+        asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sx), "=l"(sy) : "r"(gs + (uint32_t)p * 16u));
+        asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sz), "=l"(sw) : "r"(pbs + (uint32_t)p * 16u));
+    }
     __device__ __forceinline__ f4 geo(int w) const {
+        if (kPacked) {  // (only the code that was not converted to pairs asks for a single wall)
+            const uint32_t o = (uint32_t)(w >> 1) * 16u + (uint32_t)(w & 1) * 4u;
+            float x, y, z, ww;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(gs + o));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(gs + o + 8u));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(z) : "r"(pbs + o));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(ww) : "r"(pbs + o + 8u));
+            return f4{x, y, z, ww};
+        }
         if (STAGE == 2) {
             float4 v = __ldg(reinterpret_cast<const float4 *>(g) + w);
             return f4{v.x, v.y, v.z, v.w};
@@ -321,6 +339,27 @@ __device__ __forceinline__ bool coop_shadow(const Scene &sc, bool pending, const
             first = 0;  // every intersect() result (<= inf) is < lim: wall 0 blocks
         } else {
             const float lim_m = b.lim * kSlack;
+            if constexpr (Scene::kPacked) {
+                // 32 lanes x one pair record = the same 64 consecutive walls per iteration, walls 2p and 2p+1 per lane
+                const int np = (n + 1) >> 1;
+                for (int pbase = 0; pbase < np; pbase += 32) {
+                    const int pi = pbase + (int)lane;
+                    bool k0 = false, k1 = false;
+                    if (pi < np) {
+                        const WallTest2 t = wall_test2(sc, pi, b.sx, b.sy, b.dx, b.ndy);
+                        bool p0, p1;
+                        wall_pass2(t, lim_m, p0, p1);
+                        k0 = p0 && intersect_exact(pair_lo(t.num1), pair_lo(t.num2), -pair_lo(t.ndotP)) < b.lim;
+                        k1 = p1 && intersect_exact(pair_hi(t.num1), pair_hi(t.num2), -pair_hi(t.ndotP)) < b.lim;
+                    }
+                    const unsigned m0 = __ballot_sync(kFull, k0), m1 = __ballot_sync(kFull, k1);
+                    if (m0 | m1) {
+                        const int f0 = m0 ? 2 * (__ffs(m0) - 1) : (1 << 30), f1 = m1 ? 2 * (__ffs(m1) - 1) + 1 : (1 << 30);
+                        first = 2 * pbase + min(f0, f1);
+                        break;
+                    }
+                }
+            } else
             for (int base = 0; base < n; base += 64) {
                 const int w0 = base + (int)lane, w1 = w0 + 32;
                 const bool k0 = w0 < n && shadow_blocked_by(sc.geo(w0), b, lim_m);
@@ -355,7 +394,12 @@ __device__ __forceinline__ SceneView<STAGE, GRID, FAST> stage_scene(const TraceL
             fence_barrier_init();
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && (FAST & 4)) {  // PACKED (stage 1 only): the two pair planes instead of the endpoint plane
+            const uint32_t pair_bytes = (uint32_t)((a.n_walls + 1) >> 1) * 16u;
+            mbar_arrive_expect_tx(bar, 2u * pair_bytes);
+            bulk_copy_g2s(s_geo, a.pair_a, pair_bytes, bar);
+            bulk_copy_g2s(reinterpret_cast<unsigned char *>(s_geo) + pair_bytes, a.pair_b, pair_bytes, bar);
+        } else if (threadIdx.x == 0) {
             const uint32_t geo_bytes = (uint32_t)a.n_walls * 16u;
             const uint32_t m1_bytes = ((uint32_t)a.n_walls * 8u + 15u) & ~15u;  // planes are padded to 16 B
             const uint32_t total = STAGE == 0 ? geo_bytes * 2u + m1_bytes : geo_bytes;
@@ -384,6 +428,7 @@ __device__ __forceinline__ SceneView<STAGE, GRID, FAST> stage_scene(const TraceL
     sc.gs = base;
     sc.m0s = base + (uint32_t)a.n_walls * 16u;
     sc.m1s = base + (uint32_t)a.n_walls * 32u;
+    sc.pbs = base + (uint32_t)((a.n_walls + 1) >> 1) * 16u;
     sc.ba = a.band_abs;
     sc.n = a.n_walls;
     sc.nb = a.band_total;
@@ -407,7 +452,8 @@ constexpr int trace_min_blocks(int maxt, int bands, int stage, bool grid, int fa
 
 template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false, int FAST = 0>
 __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRID, FAST)) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
-    static_assert(FAST == 0 || (OPAQUE && !COUNT && !HITS && !GRID && !COOP && STAGE == 0), "FAST variants: production small-scene kernels");
+    static_assert(FAST == 0 || FAST == 4 || (OPAQUE && !COUNT && !HITS && !GRID && !COOP && STAGE == 0), "FAST 1/3: production small-scene kernels");
+    static_assert(FAST != 4 || (STAGE == 1 && COOP && !GRID && !COUNT && !HITS), "PACKED: production staged-endpoint kernels");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SceneView<STAGE, GRID, FAST> sc = stage_scene<STAGE, GRID, FAST>(a, smem_raw);
     SpecConsts spec_c = {0.f, 0.f};
@@ -534,11 +580,12 @@ __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRI
 // nearest-hit loop once and then, for every listener, only the listener pieces: the direct crossing test
 // before the advance, and the next-event estimate with its shadow ray after it.  Listener l deposits into its
 // own histogram.  Result per listener: identical to a single-listener trace (same pieces, same order).
-template <bool COUNT, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false>
+template <bool COUNT, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false, int FAST = 0>
 __global__ void __launch_bounds__(MAXT) trace_listeners_kernel(const __grid_constant__ TraceLaunch a) {
+    static_assert(FAST == 0 || (FAST == 4 && STAGE == 1 && COOP && !GRID && !COUNT), "PACKED: production staged-endpoint kernels");
     constexpr int BANDS = 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SceneView<STAGE, GRID, 0> sc = stage_scene<STAGE, GRID, 0>(a, smem_raw);
+    const SceneView<STAGE, GRID, FAST> sc = stage_scene<STAGE, GRID, FAST>(a, smem_raw);
 
     const unsigned lane = threadIdx.x & 31u;
     const long long rays_per_frame = a.ray_end - a.ray_begin;
@@ -708,6 +755,12 @@ cudaError_t resident_blocks(const void *fn, int threads, size_t smem, int *block
 // Small scenes (all planes in shared memory, several CTAs per SM): per-thread shadow walk, 256 threads.
 // Large scenes: warp-cooperative shadow rays; one CTA of 1024 threads per SM once the endpoint plane
 // takes more than half of shared memory.
+// stage 1 production kernels with the packed-FP32 wall scans
+template <int BANDS>
+KernelChoice pick_packed(bool big_block) {
+    if (big_block) return {(const void *)trace_deposit_kernel<BANDS, false, false, 1, 1024, true, false, false, 4>, 1024};
+    return {(const void *)trace_deposit_kernel<BANDS, false, false, 1, 256, true, false, false, 4>, 256};
+}
 template <int BANDS, bool COUNT, bool HITS>
 KernelChoice pick_kernel(int stage, bool big_block, bool coop) {
     if (stage == 0) {
@@ -743,7 +796,8 @@ KernelChoice pick_listeners(int stage, bool big_block, bool coop) {
 }
 // The OPAQUE instantiations exist for the production mode only (no test counters, no hit list).
 template <int BANDS>
-KernelChoice pick_mode(bool count, bool hits, bool opaque, int stage, bool big, bool coop, int fast) {
+KernelChoice pick_mode(bool count, bool hits, bool opaque, int stage, bool big, bool coop, int fast, bool packed) {
+    if (packed && stage == 1 && !count && !hits) return pick_packed<BANDS>(big);
     if (hits) return count ? pick_kernel<BANDS, true, true>(stage, big, coop) : pick_kernel<BANDS, false, true>(stage, big, coop);
     if (count) return pick_kernel<BANDS, true, false>(stage, big, coop);
     // Large scenes spend their time in the wall loops; there the smaller scatter code changes nothing measurable (the
@@ -751,7 +805,11 @@ KernelChoice pick_mode(bool count, bool hits, bool opaque, int stage, bool big, 
     if (opaque && stage == 0) return pick_kernel_opaque<BANDS>(coop, fast);
     return pick_kernel<BANDS, false, false>(stage, big, coop);
 }
-KernelChoice pick_listeners_mode(bool count, bool opaque, int stage, bool big, bool coop) {
+KernelChoice pick_listeners_mode(bool count, bool opaque, int stage, bool big, bool coop, bool packed) {
+    if (packed && stage == 1 && !count) {
+        if (big) return {(const void *)trace_listeners_kernel<false, 1, 1024, true, false, false, 4>, 1024};
+        return {(const void *)trace_listeners_kernel<false, 1, 256, true, false, false, 4>, 256};
+    }
     if (count) return pick_listeners<true>(stage, big, coop);
     (void)opaque;  // the listener kernels spend their time in per-listener work, not in the scatter step
     return pick_listeners<false>(stage, big, coop);
@@ -793,8 +851,12 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     const char *nf = getenv("RAR_NO_FAST");
     const bool no_fast = nf != nullptr && nf[0] == '1';
     const int fast = (a.spec_ok && !no_fast) ? (a.n_walls == 4 ? 3 : 1) : 0;
+    // PACKED: the staged-endpoint production kernels scan two walls per packed FP32 instruction (RAR_NO_PACKED=1: scalar)
+    const char *np_env = getenv("RAR_NO_PACKED");
+    const bool packed = !(np_env != nullptr && np_env[0] == '1') && !count_tests && !hits && a.pair_a != nullptr;
+    const size_t stage1_bytes = packed ? (size_t)((a.n_walls + 1) / 2) * 32 : geo_bytes;
     struct Cand { int stage; bool big; size_t smem; };
-    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes}, {1, false, 16 + geo_bytes}, {1, true, 16 + geo_bytes}, {2, false, 16}};
+    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes}, {1, false, 16 + stage1_bytes}, {1, true, 16 + stage1_bytes}, {2, false, 16}};
     KernelChoice k{nullptr, 0};
     size_t smem = 0;
     bool big_block = false;
@@ -820,9 +882,9 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
         const bool coop = c.stage != 0 || a.n_walls >= kCoopMinWalls;
         KernelChoice kc;
         const bool opq = a.opaque != 0;
-        if (a.n_listeners > 0) kc = pick_listeners_mode(count_tests, opq, c.stage, c.big, coop);
-        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, opq, c.stage, c.big, coop, fast)
-                               : pick_mode<1>(count_tests, hits, opq, c.stage, c.big, coop, fast);
+        if (a.n_listeners > 0) kc = pick_listeners_mode(count_tests, opq, c.stage, c.big, coop, packed);
+        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, opq, c.stage, c.big, coop, fast, packed)
+                               : pick_mode<1>(count_tests, hits, opq, c.stage, c.big, coop, fast, packed);
         int blocks = 0;
         cudaError_t e = resident_blocks(kc.fn, kc.max_threads, c.smem, &blocks);
         if (e != cudaSuccess) return e;

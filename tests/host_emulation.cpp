@@ -15,6 +15,7 @@ struct HostSceneT {
     static constexpr bool kPeelFirstBatch = !GRID;  // exercise the small-scene filter of the nearest-hit scan
     static constexpr bool kSpec = (FAST & 1) != 0;   // the range-checked-once pieces (on the host: plain IEEE ops)
     static constexpr bool kFixed4 = (FAST & 2) != 0; // exactly four walls, no loops
+    static constexpr bool kPacked = false;           // (the packed-FP32 wall scans are device code)
     rar::GridView gv;
     const rar::GridView &grid() const { return gv; }
     rar::f4 grid_geo(uint32_t i) const { return gv.item_geo[i]; }

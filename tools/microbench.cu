@@ -35,6 +35,39 @@ __global__ void __launch_bounds__(256) k(float *out, const float *in) {
     if (s == 12345.678f || cnt == -1) out[0] = s;
 }
 
+// Packed FP32 (sm_100: fma/add/mul .f32x2 -> FFMA2 / FADD2 / FMUL2, two IEEE binary32 results per lane and instruction).
+// mode 0: FFMA2 three-register; 1: FMUL2; 2: FADD2; 3: FFMA2 + scalar FSETP interleaved 1:1; 4: FFMA2 + FFMA 1:1
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k2(float *out, const float *in) {
+    const unsigned long long a = pk(in[0], in[0]), b = pk(in[1], in[1]);
+    const float d = in[3], as = in[0], bs = in[1];
+    unsigned long long x[8];
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { x[j] = pk(threadIdx.x * 1e-3f + j, threadIdx.x * 2e-3f + j); y[j] = threadIdx.x * 3e-3f + j; }
+    int cnt = 0;
+    for (int i = 0; i < ITER; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (MODE == 0 || MODE == 3 || MODE == 4) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[j]) : "l"(a), "l"(b));
+                if (MODE == 1) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(x[j]) : "l"(a));
+                if (MODE == 2) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x[j]) : "l"(b));
+                if (MODE == 3) cnt += (__uint_as_float((unsigned)x[j]) > d) ? 1 : 0;
+                if (MODE == 4) y[j] = __fmaf_rn(y[j], as, bs);
+            }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += __uint_as_float((unsigned)x[j]) + __uint_as_float((unsigned)(x[j] >> 32)) + y[j];
+    if (s == 12345.678f || cnt == -1) out[0] = s;
+}
+
 // shared-memory broadcast LDS.128 rate: every lane reads the same 16 bytes
 __global__ void __launch_bounds__(256) lds_bcast(float *out, int n) {
     __shared__ float4 buf[1024];
@@ -133,6 +166,18 @@ int main() {
     for (int m = 0; m < 6; m++)
         printf("%-18s %8.3f ms  %7.2f T lane-ops/s  (%.3f warp-inst/clk/SMSP at 1.965 GHz)\n", names[m], ms[m],
                ops / (ms[m] * 1e-3) / 1e12, ops / 32.0 / (ms[m] * 1e-3) / (sms * 4 * 1.965e9));
+    {
+        const char *n2[] = {"FFMA2 3-register", "FMUL2 register", "FADD2 register", "FFMA2+FSETP+IADD", "FFMA2+FFMA 1:1"};
+        double t[5];
+        t[0] = time_ms([&] { k2<0><<<blocks, 256>>>(out, in); });
+        t[1] = time_ms([&] { k2<1><<<blocks, 256>>>(out, in); });
+        t[2] = time_ms([&] { k2<2><<<blocks, 256>>>(out, in); });
+        t[3] = time_ms([&] { k2<3><<<blocks, 256>>>(out, in); });
+        t[4] = time_ms([&] { k2<4><<<blocks, 256>>>(out, in); });
+        for (int m = 0; m < 5; m++)  // `ops` counts packed INSTRUCTIONS per lane here: each is two FP32 results
+            printf("%-18s %8.3f ms  %7.2f T packed lane-instr/s = %7.2f T FP32 results/s  (%.3f packed warp-inst/clk/SMSP)\n", n2[m], t[m],
+                   ops / (t[m] * 1e-3) / 1e12, 2.0 * ops / (t[m] * 1e-3) / 1e12, ops / 32.0 / (t[m] * 1e-3) / (sms * 4 * 1.965e9));
+    }
     double l = time_ms([&] { lds_bcast<<<blocks, 256>>>(out, 3); });
     const double lds = (double)blocks * 256 * ITER * 16.0;
     printf("LDS.128 broadcast  %8.3f ms  %7.2f T lane-loads/s  (%.3f warp-LDS/clk/SM)\n", l, lds / (l * 1e-3) / 1e12,
