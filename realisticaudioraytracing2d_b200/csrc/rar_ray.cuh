@@ -210,6 +210,13 @@ __device__ __forceinline__ void wall_pass2(const WallTest2 &t, float bound_m, bo
     p0 = (fabsf(pair_lo(c1)) <= fabsf(pair_lo(t.ndotP))) & (fabsf(pair_lo(c2)) <= fabsf(pair_lo(nr)));
     p1 = (fabsf(pair_hi(c1)) <= fabsf(pair_hi(t.ndotP))) & (fabsf(pair_hi(c2)) <= fabsf(pair_hi(nr)));
 }
+// wall_pass_unbounded for a pair: "num1 and dotP of the same sign" reads "num1 and ndotP of opposite signs"
+__device__ __forceinline__ void wall_pass_unbounded2(const WallTest2 &t, bool &p0, bool &p1) {
+    const uint64_t c1 = fma2(pair_bc(2.0f), t.num2, t.ndotP);
+    const uint64_t x = t.num1 ^ t.ndotP;  // sign bits: bit 31 (wall 2p), bit 63 (wall 2p+1)
+    p0 = (fabsf(pair_lo(c1)) <= fabsf(pair_lo(t.ndotP))) & ((int)(unsigned)x < 0);
+    p1 = (fabsf(pair_hi(c1)) <= fabsf(pair_hi(t.ndotP))) & ((long long)x < 0);
+}
 #endif
 
 // ---- optional uniform grid over the walls (RAR_FLAG_USE_GRID) -------------------------------------------
@@ -386,7 +393,21 @@ RAR_HD void nearest_hit(const Scene &sc, float ox, float oy, float dx, float dy,
         }                                                            \
     }
 #ifdef __CUDACC__
-    if constexpr (Scene::kPacked) {
+    if constexpr (Scene::kPacked && Scene::kFixed4) {  // exactly four walls = two pair records, no bound yet
+        const WallTest2 ta = wall_test2(sc, 0, ox, oy, dx, ndy), tb = wall_test2(sc, 1, ox, oy, dx, ndy);
+        bool p0, p1, p2, p3;
+        wall_pass_unbounded2(ta, p0, p1);
+        wall_pass_unbounded2(tb, p2, p3);
+        if (p0 | p1 | p2 | p3) {
+            if (p0) RAR_NEAREST_EXACT2(ta, lo, 0)
+            if (p1) RAR_NEAREST_EXACT2(ta, hi, 1)
+            if (p2) RAR_NEAREST_EXACT2(tb, lo, 2)
+            if (p3) RAR_NEAREST_EXACT2(tb, hi, 3)
+        }
+        closest_out = closest;
+        hit_out = hit;
+        return;
+    } else if constexpr (Scene::kPacked) {
         // two pair records = four walls per iteration, in wall order (ties go to the lower index, as in the scalar scan)
         const int np = (n + 1) >> 1;
         int p = 0;
@@ -494,6 +515,23 @@ RAR_HD bool check_vis(const Scene &sc, const ShadowRay &q, int *tests) {
     }
     const float lim_m = q.lim * kSlack;
     constexpr bool SP = Scene::kSpec;
+#ifdef __CUDACC__
+    if constexpr (Scene::kFixed4 && Scene::kPacked) {
+        const WallTest2 ta = wall_test2(sc, 0, q.sx, q.sy, q.dx, q.ndy), tb = wall_test2(sc, 1, q.sx, q.sy, q.dx, q.ndy);
+        bool p0, p1, p2, p3;
+        wall_pass2(ta, lim_m, p0, p1);
+        wall_pass2(tb, lim_m, p2, p3);
+        int first4 = -1;
+        if (p0 | p1 | p2 | p3) {
+            if (p3 && intersect_exact<SP>(pair_hi(tb.num1), pair_hi(tb.num2), -pair_hi(tb.ndotP)) < q.lim) first4 = 3;
+            if (p2 && intersect_exact<SP>(pair_lo(tb.num1), pair_lo(tb.num2), -pair_lo(tb.ndotP)) < q.lim) first4 = 2;
+            if (p1 && intersect_exact<SP>(pair_hi(ta.num1), pair_hi(ta.num2), -pair_hi(ta.ndotP)) < q.lim) first4 = 1;
+            if (p0 && intersect_exact<SP>(pair_lo(ta.num1), pair_lo(ta.num2), -pair_lo(ta.ndotP)) < q.lim) first4 = 0;
+        }
+        if (tests) *tests = first4 >= 0 ? first4 + 1 : 4;
+        return first4 < 0;
+    }
+#endif
     if constexpr (Scene::kFixed4) {  // exactly four walls: one batch, no loop
         const WallTest t0 = wall_test(sc.geo(0), q.sx, q.sy, q.dx, q.ndy);
         const WallTest t1 = wall_test(sc.geo(1), q.sx, q.sy, q.dx, q.ndy);

@@ -105,7 +105,7 @@ struct SceneView {
     const f4 *m0;
     const f2 *m1;
     uint32_t gs, m0s, m1s;  // shared-space addresses of the staged planes (STAGE 0: all three, STAGE 1: gs)
-    uint32_t pbs;           // kPacked: gs is pair_a, pbs is pair_b
+    uint32_t pas, pbs;      // kPacked: the pair planes (STAGE 1: pair_a sits where the endpoint plane would, pas == gs)
     const float *ba;
     int n, nb, boff;
     GridView gv;
@@ -117,15 +117,15 @@ struct SceneView {
     __device__ __forceinline__ int n_walls() const { return n; }
     // pair record p: (x0 x1), (y0 y1) from pair_a; (ex0 ex1), (ey0 ey1) from pair_b -- one LDS.128 each
     __device__ __forceinline__ void pair(int p, uint64_t &sx, uint64_t &sy, uint64_t &sz, uint64_t &sw) const {
-        asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sx), "=l"(sy) : "r"(gs + (uint32_t)p * 16u));
+        asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sx), "=l"(sy) : "r"(pas + (uint32_t)p * 16u));
         asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sz), "=l"(sw) : "r"(pbs + (uint32_t)p * 16u));
     }
     __device__ __forceinline__ f4 geo(int w) const {
-        if (kPacked) {  // (only the code that was not converted to pairs asks for a single wall)
+        if (kPacked && STAGE == 1) {  // (only code that was not converted to pairs asks for a single wall)
             const uint32_t o = (uint32_t)(w >> 1) * 16u + (uint32_t)(w & 1) * 4u;
             float x, y, z, ww;
-            asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(gs + o));
-            asm("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(gs + o + 8u));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(pas + o));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(pas + o + 8u));
             asm("ld.shared.f32 %0, [%1];" : "=f"(z) : "r"(pbs + o));
             asm("ld.shared.f32 %0, [%1];" : "=f"(ww) : "r"(pbs + o + 8u));
             return f4{x, y, z, ww};
@@ -394,17 +394,19 @@ __device__ __forceinline__ SceneView<STAGE, GRID, FAST> stage_scene(const TraceL
             fence_barrier_init();
         }
         __syncthreads();
-        if (threadIdx.x == 0 && (FAST & 4)) {  // PACKED (stage 1 only): the two pair planes instead of the endpoint plane
-            const uint32_t pair_bytes = (uint32_t)((a.n_walls + 1) >> 1) * 16u;
-            mbar_arrive_expect_tx(bar, 2u * pair_bytes);
-            bulk_copy_g2s(s_geo, a.pair_a, pair_bytes, bar);
-            bulk_copy_g2s(reinterpret_cast<unsigned char *>(s_geo) + pair_bytes, a.pair_b, pair_bytes, bar);
-        } else if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) {
             const uint32_t geo_bytes = (uint32_t)a.n_walls * 16u;
             const uint32_t m1_bytes = ((uint32_t)a.n_walls * 8u + 15u) & ~15u;  // planes are padded to 16 B
-            const uint32_t total = STAGE == 0 ? geo_bytes * 2u + m1_bytes : geo_bytes;
+            const uint32_t pair_bytes = (FAST & 4) ? (uint32_t)((a.n_walls + 1) >> 1) * 16u : 0u;
+            // PACKED: stage 1 holds the two pair planes INSTEAD of the endpoint plane, stage 0 holds them behind the others
+            const uint32_t total = STAGE == 0 ? geo_bytes * 2u + m1_bytes + 2u * pair_bytes : ((FAST & 4) ? 2u * pair_bytes : geo_bytes);
             mbar_arrive_expect_tx(bar, total);
-            bulk_copy_g2s(s_geo, a.geo, geo_bytes, bar);
+            unsigned char *s_pairs = STAGE == 0 ? reinterpret_cast<unsigned char *>(s_mat1) + m1_bytes : reinterpret_cast<unsigned char *>(s_geo);
+            if (FAST & 4) {
+                bulk_copy_g2s(s_pairs, a.pair_a, pair_bytes, bar);
+                bulk_copy_g2s(s_pairs + pair_bytes, a.pair_b, pair_bytes, bar);
+            }
+            if (STAGE == 0 || !(FAST & 4)) bulk_copy_g2s(s_geo, a.geo, geo_bytes, bar);
             if (STAGE == 0) {
                 bulk_copy_g2s(s_mat0, a.mat0, geo_bytes, bar);
                 bulk_copy_g2s(s_mat1, a.mat1, m1_bytes, bar);
@@ -428,7 +430,8 @@ __device__ __forceinline__ SceneView<STAGE, GRID, FAST> stage_scene(const TraceL
     sc.gs = base;
     sc.m0s = base + (uint32_t)a.n_walls * 16u;
     sc.m1s = base + (uint32_t)a.n_walls * 32u;
-    sc.pbs = base + (uint32_t)((a.n_walls + 1) >> 1) * 16u;
+    sc.pas = STAGE == 0 ? base + (uint32_t)a.n_walls * 32u + (((uint32_t)a.n_walls * 8u + 15u) & ~15u) : base;
+    sc.pbs = sc.pas + (uint32_t)((a.n_walls + 1) >> 1) * 16u;
     sc.ba = a.band_abs;
     sc.n = a.n_walls;
     sc.nb = a.band_total;
@@ -452,8 +455,9 @@ constexpr int trace_min_blocks(int maxt, int bands, int stage, bool grid, int fa
 
 template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false, int FAST = 0>
 __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRID, FAST)) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
-    static_assert(FAST == 0 || FAST == 4 || (OPAQUE && !COUNT && !HITS && !GRID && !COOP && STAGE == 0), "FAST 1/3: production small-scene kernels");
+    static_assert(FAST == 0 || FAST == 4 || (OPAQUE && !COUNT && !HITS && !GRID && !COOP && STAGE == 0), "FAST 1/3/7: production small-scene kernels");
     static_assert(FAST != 4 || (STAGE == 1 && COOP && !GRID && !COUNT && !HITS), "PACKED: production staged-endpoint kernels");
+    static_assert(FAST <= 4 || FAST == 7, "PACKED small-scene kernel: the four-wall variant only");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SceneView<STAGE, GRID, FAST> sc = stage_scene<STAGE, GRID, FAST>(a, smem_raw);
     SpecConsts spec_c = {0.f, 0.f};
@@ -778,6 +782,7 @@ KernelChoice pick_kernel(int stage, bool big_block, bool coop) {
 template <int BANDS>
 KernelChoice pick_kernel_opaque(bool coop, int fast) {
     if (coop) return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, true, false, true>, 256};
+    if (fast == 7) return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, false, false, true, 7>, 256};
     if (fast == 3) return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, false, false, true, 3>, 256};
     if (fast == 1) return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, false, false, true, 1>, 256};
     return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, false, false, true>, 256};
@@ -855,8 +860,9 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     const char *np_env = getenv("RAR_NO_PACKED");
     const bool packed = !(np_env != nullptr && np_env[0] == '1') && !count_tests && !hits && a.pair_a != nullptr;
     const size_t stage1_bytes = packed ? (size_t)((a.n_walls + 1) / 2) * 32 : geo_bytes;
+    const int fast0 = (fast == 3 && packed) ? 7 : fast;  // the four-wall kernel with packed wall tests (pair planes staged too)
     struct Cand { int stage; bool big; size_t smem; };
-    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes}, {1, false, 16 + stage1_bytes}, {1, true, 16 + stage1_bytes}, {2, false, 16}};
+    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes + (fast0 == 7 ? (size_t)64 : 0)}, {1, false, 16 + stage1_bytes}, {1, true, 16 + stage1_bytes}, {2, false, 16}};
     KernelChoice k{nullptr, 0};
     size_t smem = 0;
     bool big_block = false;
@@ -883,8 +889,8 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
         KernelChoice kc;
         const bool opq = a.opaque != 0;
         if (a.n_listeners > 0) kc = pick_listeners_mode(count_tests, opq, c.stage, c.big, coop, packed);
-        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, opq, c.stage, c.big, coop, fast, packed)
-                               : pick_mode<1>(count_tests, hits, opq, c.stage, c.big, coop, fast, packed);
+        else kc = a.bands == 8 ? pick_mode<8>(count_tests, hits, opq, c.stage, c.big, coop, fast0, packed)
+                               : pick_mode<1>(count_tests, hits, opq, c.stage, c.big, coop, fast0, packed);
         int blocks = 0;
         cudaError_t e = resident_blocks(kc.fn, kc.max_threads, c.smem, &blocks);
         if (e != cudaSuccess) return e;

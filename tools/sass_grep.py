@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Counts the SASS mnemonics that evidence the design per kernel of the built objects (no GPU needed):
 UBLKCP (1-D TMA bulk copy), SYNCS (mbarrier), REDUX (warp reduce), MATCH (match_any), ATOMG/REDG/RED (global atomics),
-MUFU, LDS, and the instruction count.
+FFMA2 / FMUL2 / FADD2 (packed FP32), UBLKPF (bulk L2 prefetch), MUFU, LDS, and the instruction count.
 
     python tools/sass_grep.py > profiles/r02_sass_grep.txt
 """
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "realisticaudioraytracing2d_b200", "_obj")
-KEYS = ["UBLKCP", "UTMALDG", "SYNCS", "REDUX", "MATCH", "ATOMG", "REDG", "MUFU", "LDS", "LDG", "FCHK", "BSSY"]
+KEYS = ["UBLKCP", "UBLKPF", "UTMALDG", "SYNCS", "REDUX", "MATCH", "ATOMG", "REDG", "FFMA2", "FMUL2", "FADD2", "MUFU", "LDS", "LDG", "FCHK", "BSSY"]
 
 
 def main():
