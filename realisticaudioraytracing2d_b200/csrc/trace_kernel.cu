@@ -432,6 +432,9 @@ __device__ __forceinline__ SceneView<STAGE, GRID, FAST> stage_scene(const TraceL
     sc.m1s = base + (uint32_t)a.n_walls * 32u;
     sc.pas = STAGE == 0 ? base + (uint32_t)a.n_walls * 32u + (((uint32_t)a.n_walls * 8u + 15u) & ~15u) : base;
     sc.pbs = sc.pas + (uint32_t)((a.n_walls + 1) >> 1) * 16u;
+    // (opaque to the compiler from here on: with 64 registers it preferred to RE-DERIVE pbs from the launch
+    // arguments inside the wall loop -- seven instructions per iteration, 13 % of the maze kernel -- to holding it)
+    if (FAST & 4) asm volatile("" : "+r"(sc.pas), "+r"(sc.pbs));
     sc.ba = a.band_abs;
     sc.n = a.n_walls;
     sc.nb = a.band_total;

@@ -106,7 +106,7 @@ def main():
             t = text(*outer).strip()
             phase = "loop head (any-ray-alive vote, per-bounce set-up)" if ("__any_sync" in t or "i < max_b" in t or "else if (alive)" in t or "if (alive) {" in t or "want_shadow" in t) \
                 else "tile loop, claim, debug rows, tail"
-        if phase in ("nearest hit", "shadow ray") and any("intersect_exact" in t or "_EXACT(" in t for t in lines):
+        if phase in ("nearest hit", "shadow ray") and any("intersect_exact" in t or "_EXACT(" in t or "_EXACT2(" in t for t in lines):
             phase += ": exact evaluation of survivors"
         elif phase in ("nearest hit", "shadow ray"):
             phase += ": wall filters"

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-2 profiling pass (run on the GPU box through gpurun; artefacts land in gpurun_out/, summaries are made from
+# Round-2 profiling pass (run on the GPU box through gpurun -- in two calls, tools/profile_round2b.sh holds the c2 captures
+# and the launch list: gpurun brings back at most 64 MiB per call and six full captures exceed that; artefacts land in gpurun_out/, summaries are made from
 # them by tools/summarize_profiles.py r02).  Every capture follows a plain run of the same command that exited 0.
 set -u
 out=gpurun_out

@@ -58,7 +58,7 @@ JOBS = {
                   ("prof_grid_final", "ncu_trace_grid", "trace_deposit_kernel on the 10 000-wall maze, RAR_FLAG_USE_GRID (RAR_GRID=1 tools/run_trace.py maze)"),
                   ("prof_cmac_final", "ncu_cmac", "stream_cmac_kernel on BASELINE config 5 (tools/run_trace.py conv)")],
     # tools/profile_round2.sh
-    "r02": [("r02_c2", "ncu_trace_c2", "trace_deposit_kernel<..., FAST=3> on BASELINE config 2 (tools/run_trace.py c2): four-wall, range-checked-once variant"),
+    "r02": [("r02_c2", "ncu_trace_c2", "trace_deposit_kernel<..., FAST=7> on BASELINE config 2 (tools/run_trace.py c2): four-wall, range-checked-once variant with packed FP32 wall tests"),
             ("r02_c2_guarded", "ncu_trace_c2_guarded", "the same dispatch with RAR_NO_FAST=1: the kernel with a guard around every division / square root"),
             ("r02_maze8", "ncu_trace_maze8", "trace_deposit_kernel on the 10 000-wall maze, 8 bands, brute force (tools/run_trace.py maze8)"),
             ("r02_c1", "ncu_trace_c1", "trace_deposit_kernel on BASELINE config 1, one 15 000-ray frame of SmollRoom (tools/run_trace.py c1)"),
