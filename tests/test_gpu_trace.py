@@ -572,3 +572,67 @@ def test_asynchronous_ir_readback(ctx, oracle):
     assert not ctx.ir_read_end(t, 16).any()
     with pytest.raises(_capi.RarError):
         ctx.ir_read_end(t, 16)                              # the ticket was released
+
+
+def _adversarial_walls(n, seed):
+    """A maze plus walls chosen to hit the zeros of the filter: axis-parallel walls through the source's coordinates
+    (num1 = 0 or num2 = 0 for whole fans of rays, dotP = 0 for the axis-parallel rays), zero-length walls, duplicates,
+    and an odd total (the last pair record holds one wall and a NaN)."""
+    sc = scenes.maze(n_segments=n, ray_count=60_000, max_bounces=12, bands=8, seed=seed)
+    walls = sc.walls.copy()
+    sx, sy = sc.source
+    k = 0
+    for (a, b) in (((sx - 7.0, sy), (sx - 3.0, sy)), ((sx + 2.0, sy), (sx + 9.0, sy)),      # on the source's horizontal line
+                   ((sx, sy + 1.5), (sx, sy + 6.0)), ((sx, sy - 8.0), (sx, sy - 2.5)),      # ... vertical line
+                   ((sx + 4.0, sy + 4.0), (sx + 4.0, sy + 4.0)),                            # zero length
+                   ((sx - 5.0, sy - 5.0), (sx - 1.0, sy - 1.0))):                           # on a diagonal through the source
+        w = walls[k]
+        w["start"], w["end"] = a, b
+        d = np.array(b, np.float32) - np.array(a, np.float32)
+        ln = float(np.hypot(*d))
+        w["normal"] = (-d[1] / ln, d[0] / ln) if ln > 0 else (0.0, 1.0)
+        k += 37
+    walls[5] = walls[4]                                                                      # a duplicate
+    return sc, walls
+
+
+@pytest.mark.parametrize("n,bands", [(301, 1), (1000, 8), (4001, 1)])
+def test_packed_and_scalar_wall_scans_agree(ctx, oracle, monkeypatch, n, bands):
+    """FAST bit 2 (packed FP32, two walls per instruction) against RAR_NO_PACKED=1 (scalar) and the oracle, on geometry
+    that sits on the zeros of the filter quantities -- where the packed forms carry some zeros with the other sign."""
+    sc, walls = _adversarial_walls(n, n)
+    kw = trace_kwargs(sc, bands=bands)
+    m = kw["impulse_length"]
+    ctx.set_walls(walls)
+    if bands > 1:
+        ctx.set_wall_band_absorption(sc.band_absorption)
+    out = []
+    for no_packed in ("0", "1"):
+        monkeypatch.setenv("RAR_NO_PACKED", no_packed)
+        ctx.ir_clear(0, m, bands)
+        ctx.trace(capi_params(_capi, kw), 0)
+        out.append(ctx.ir_read_fixed(0, m * bands))
+    monkeypatch.delenv("RAR_NO_PACKED")
+    want = oracle.trace(oracle_walls(oracle, walls), oracle_params(oracle, kw), band_abs=sc.band_absorption if bands > 1 else None).hist
+    assert np.array_equal(out[0], out[1])
+    assert np.array_equal(out[0], want) and np.count_nonzero(want) > 500
+
+
+def test_packed_four_wall_kernel_on_the_zeros_of_the_filter(ctx, oracle, monkeypatch):
+    """The FAST = 7 kernel (config 2's) with the source on the room's axes of symmetry and on a wall's line: rays
+    parallel to walls (dotP = 0), num1 = 0 and num2 = 0 for the first bounce of whole fans of rays."""
+    for src, lst in (((5.0, 3.0), (7.5, 3.0)), ((5.0, 0.0), (2.0, 3.0)), ((0.0, 3.0), (9.0, 5.0)), ((2.5, 1.5), (2.5, 4.5))):
+        sc = scenes.shoebox(ray_count=65536, max_bounces=24)
+        kw = trace_kwargs(sc, source=src, listener=lst)
+        m = kw["impulse_length"]
+        ctx.set_walls(sc.walls)
+        out = []
+        for no_packed in ("0", "1"):
+            monkeypatch.setenv("RAR_NO_PACKED", no_packed)
+            ctx.ir_clear(0, m, 1)
+            ctx.trace(capi_params(_capi, kw), 0)
+            out.append(ctx.ir_read_fixed(0, m))
+        monkeypatch.delenv("RAR_NO_PACKED")
+        want = oracle.trace(oracle_walls(oracle, sc.walls), oracle_params(oracle, kw)).hist
+        assert np.array_equal(out[0], out[1]), (src, lst)
+        assert np.array_equal(out[0], want), (src, lst)
