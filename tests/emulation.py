@@ -112,6 +112,16 @@ def intersect_many(rays, segs, closest):
     return out
 
 
+def pair_planes(walls):
+    """rar_layout.h pair_planes: (pair_a, pair_b), each [(n + 1) // 2][4]."""
+    walls = np.ascontiguousarray(walls)
+    n = len(walls)
+    a = np.zeros(((n + 1) // 2, 4), np.float32)
+    b = np.zeros_like(a)
+    lib().emu_pair_planes(C.c_void_p(walls.ctypes.data), n, C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+    return a, b
+
+
 def grid_digest(walls):
     """Dimensions, list length and digest of the HOST-built uniform grid (rar_layout.h build_grid)."""
     walls = np.ascontiguousarray(walls)

@@ -158,6 +158,15 @@ int emu_grid_digest(const rar_segment *walls, int n, int *nx, int *ny, long long
     return 0;
 }
 
+// the pair-record planes of the packed wall scans (rar_layout.h pair_planes)
+extern "C" __attribute__((visibility("default")))
+void emu_pair_planes(const rar_segment *walls, int n, float *pair_a, float *pair_b) {
+    std::vector<rar::f4> geo(n), m0(n);
+    std::vector<rar::f2> m1(n);
+    rar::split_walls(walls, n, geo.data(), m0.data(), m1.data());
+    rar::pair_planes(geo.data(), n, (rar::f4 *)pair_a, (rar::f4 *)pair_b);
+}
+
 // ---- FFT / partitioned overlap-save convolution: the same index logic as conv_kernels.cu ----------------
 #include <cmath>
 #include "../realisticaudioraytracing2d_b200/csrc/rar_fft.cuh"

@@ -232,3 +232,20 @@ def test_band_synthesis_with_register_transforms(oracle, bins, bands):
     assert err < 2e-6, err
     half = emulation.band_synth16(hist, bands, 0.5, taps, bins)
     assert np.linalg.norm(half - 0.5 * want) / np.linalg.norm(want) < 2e-6
+
+
+@pytest.mark.parametrize("n", [4, 7, 20])
+def test_pair_planes_layout(n):
+    """The planes the packed wall scans read: record p = walls 2p and 2p+1 component by component (start x, start y,
+    edge x, edge y); a missing second wall is NaN, which no comparison of the filter accepts."""
+    walls = scenes.maze(n_segments=max(n, 8), ray_count=64, max_bounces=2, bands=8).walls[:n].copy()
+    a, b = emulation.pair_planes(walls)
+    assert a.shape == ((n + 1) // 2, 4)
+    ex = (walls["end"][:, 0] - walls["start"][:, 0]).astype(np.float32)
+    ey = (walls["end"][:, 1] - walls["start"][:, 1]).astype(np.float32)
+    for w in range(n):
+        p, h = divmod(w, 2)
+        assert a[p, h] == walls["start"][w, 0] and a[p, 2 + h] == walls["start"][w, 1]
+        assert b[p, h] == ex[w] and b[p, 2 + h] == ey[w]
+    if n % 2:
+        assert np.isnan(a[-1, 1]) and np.isnan(a[-1, 3]) and np.isnan(b[-1, 1]) and np.isnan(b[-1, 3])
