@@ -63,6 +63,7 @@ JOBS = {
             ("r02_maze8", "ncu_trace_maze8", "trace_deposit_kernel on the 10 000-wall maze, 8 bands, brute force (tools/run_trace.py maze8)"),
             ("r02_c1", "ncu_trace_c1", "trace_deposit_kernel on BASELINE config 1, one 15 000-ray frame of SmollRoom (tools/run_trace.py c1)"),
             ("r02_band_synth", "ncu_band_synth", "band_synth_kernel (the first, shared-memory-FFT synthesis kernel; RAR_NO_FAST_SYNTH=1 now): 16 banded slots x 480 000 bins x 8 bands in one launch (tools/run_bench_leg.py banded)"),
+            ("r02_listeners", "ncu_listeners", "trace_listeners_kernel (fused listeners, packed cooperative shadow scans): 128 listeners x 2^18 rays x 5 bounces, 2 000 walls (tools/run_listeners.py)"),
             ("r02_band_synth16", "ncu_band_synth16", "band_synth16_kernel (production synthesis kernel, register transforms): 16 banded slots x 480 000 bins x 8 bands in one launch (tools/run_bench_leg.py banded)")],
 }
 
