@@ -104,6 +104,7 @@ struct SceneView {
     const f4 *g;
     const f4 *m0;
     const f2 *m1;
+    const f4 *pa, *pb;      // kPacked, STAGE 2: the pair planes in global memory
     uint32_t gs, m0s, m1s;  // shared-space addresses of the staged planes (STAGE 0: all three, STAGE 1: gs)
     uint32_t pas, pbs;      // kPacked: the pair planes (STAGE 1: pair_a sits where the endpoint plane would, pas == gs)
     const float *ba;
@@ -117,11 +118,16 @@ struct SceneView {
     __device__ __forceinline__ int n_walls() const { return n; }
     // pair record p: (x0 x1), (y0 y1) from pair_a; (ex0 ex1), (ey0 ey1) from pair_b -- one LDS.128 each
     __device__ __forceinline__ void pair(int p, uint64_t &sx, uint64_t &sy, uint64_t &sz, uint64_t &sw) const {
+        if (STAGE == 2) {  // read-only global path: warp-broadcast in the nearest-hit scan, coalesced in the cooperative one
+            const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(pa) + p), b = __ldg(reinterpret_cast<const ulonglong2 *>(pb) + p);
+            sx = a.x; sy = a.y; sz = b.x; sw = b.y;
+            return;
+        }
         asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sx), "=l"(sy) : "r"(pas + (uint32_t)p * 16u));
         asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(sz), "=l"(sw) : "r"(pbs + (uint32_t)p * 16u));
     }
     __device__ __forceinline__ f4 geo(int w) const {
-        if (kPacked && STAGE == 1) {  // (only code that was not converted to pairs asks for a single wall)
+        if (kPacked && STAGE == 1) {  // (only code that was not converted to pairs asks for a single wall: none at present)
             const uint32_t o = (uint32_t)(w >> 1) * 16u + (uint32_t)(w & 1) * 4u;
             float x, y, z, ww;
             asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(pas + o));
@@ -419,6 +425,8 @@ __device__ __forceinline__ SceneView<STAGE, GRID, FAST> stage_scene(const TraceL
     SceneView<STAGE, GRID, FAST> sc;
     sc.gv = a.grid;
     sc.g = STAGE < 2 ? s_geo : a.geo;
+    sc.pa = a.pair_a;
+    sc.pb = a.pair_b;
     sc.m0 = STAGE == 0 ? s_mat0 : a.mat0;
     sc.m1 = STAGE == 0 ? s_mat1 : a.mat1;
     // The plain-asm shared loads carry no memory dependence of their own.  Their addresses derive from a value that
@@ -459,7 +467,7 @@ constexpr int trace_min_blocks(int maxt, int bands, int stage, bool grid, int fa
 template <int BANDS, bool COUNT, bool HITS, int STAGE, int MAXT, bool COOP, bool GRID = false, bool OPAQUE = false, int FAST = 0>
 __global__ void __launch_bounds__(MAXT, trace_min_blocks(MAXT, BANDS, STAGE, GRID, FAST)) trace_deposit_kernel(const __grid_constant__ TraceLaunch a) {
     static_assert(FAST == 0 || FAST == 4 || (OPAQUE && !COUNT && !HITS && !GRID && !COOP && STAGE == 0), "FAST 1/3/7: production small-scene kernels");
-    static_assert(FAST != 4 || (STAGE == 1 && COOP && !GRID && !COUNT && !HITS), "PACKED: production staged-endpoint kernels");
+    static_assert(FAST != 4 || (COOP && !GRID && !COUNT && !HITS), "PACKED: production kernels with cooperative shadow rays (256 walls and more)");
     static_assert(FAST <= 4 || FAST == 7, "PACKED small-scene kernel: the four-wall variant only");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SceneView<STAGE, GRID, FAST> sc = stage_scene<STAGE, GRID, FAST>(a, smem_raw);
@@ -764,7 +772,12 @@ cudaError_t resident_blocks(const void *fn, int threads, size_t smem, int *block
 // takes more than half of shared memory.
 // stage 1 production kernels with the packed-FP32 wall scans
 template <int BANDS>
-KernelChoice pick_packed(bool big_block) {
+KernelChoice pick_packed(int stage, bool big_block, bool opaque) {
+    if (stage == 0) {  // everything staged, 256 walls and more (cooperative shadow rays)
+        if (opaque) return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, true, false, true, 4>, 256};
+        return {(const void *)trace_deposit_kernel<BANDS, false, false, 0, 256, true, false, false, 4>, 256};
+    }
+    if (stage == 2) return {(const void *)trace_deposit_kernel<BANDS, false, false, 2, 256, true, false, false, 4>, 256};
     if (big_block) return {(const void *)trace_deposit_kernel<BANDS, false, false, 1, 1024, true, false, false, 4>, 1024};
     return {(const void *)trace_deposit_kernel<BANDS, false, false, 1, 256, true, false, false, 4>, 256};
 }
@@ -805,7 +818,7 @@ KernelChoice pick_listeners(int stage, bool big_block, bool coop) {
 // The OPAQUE instantiations exist for the production mode only (no test counters, no hit list).
 template <int BANDS>
 KernelChoice pick_mode(bool count, bool hits, bool opaque, int stage, bool big, bool coop, int fast, bool packed) {
-    if (packed && stage == 1 && !count && !hits) return pick_packed<BANDS>(big);
+    if (packed && coop && !count && !hits) return pick_packed<BANDS>(stage, big, opaque);
     if (hits) return count ? pick_kernel<BANDS, true, true>(stage, big, coop) : pick_kernel<BANDS, false, true>(stage, big, coop);
     if (count) return pick_kernel<BANDS, true, false>(stage, big, coop);
     // Large scenes spend their time in the wall loops; there the smaller scatter code changes nothing measurable (the
@@ -864,8 +877,10 @@ cudaError_t launch_trace(const TraceLaunch &a, bool count_tests, const DeviceFac
     const bool packed = !(np_env != nullptr && np_env[0] == '1') && !count_tests && !hits && a.pair_a != nullptr;
     const size_t stage1_bytes = packed ? (size_t)((a.n_walls + 1) / 2) * 32 : geo_bytes;
     const int fast0 = (fast == 3 && packed) ? 7 : fast;  // the four-wall kernel with packed wall tests (pair planes staged too)
+    // stage 0 stages the pair planes behind the others when its kernel is a packed one: four walls, or cooperative (256+ walls)
+    const bool packed0 = fast0 == 7 || (packed && a.n_walls >= kCoopMinWalls && a.n_listeners == 0);
     struct Cand { int stage; bool big; size_t smem; };
-    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes + (fast0 == 7 ? (size_t)64 : 0)}, {1, false, 16 + stage1_bytes}, {1, true, 16 + stage1_bytes}, {2, false, 16}};
+    const Cand cands[4] = {{0, false, 16 + 2 * geo_bytes + m1_bytes + (packed0 ? (size_t)((a.n_walls + 1) / 2) * 32 : 0)}, {1, false, 16 + stage1_bytes}, {1, true, 16 + stage1_bytes}, {2, false, 16}};
     KernelChoice k{nullptr, 0};
     size_t smem = 0;
     bool big_block = false;
